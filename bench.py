@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the SupCon hot path (BASELINE.json metric: fwd+bwd sim-pairs/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--n 65536] [--d 256] [--dtype bf16|f32] [--similarity cosine]
+
+One "step" = one forward + backward of the loss over one batch of synthetic
+unit-norm embeddings (value = N^2 / t).  Default workload = BASELINE.json
+configs[3], the largest single-GPU configuration the metric is quoted on:
+cosine SupCon, tau 0.07, N = 65536, d = 256, bf16 z / fp32-or-bf16 dz.  With
+--gpus R > 1 (launched by torchrun) the N rows are sharded over the ranks
+(strong scaling at fixed N): all-gather z/labels -> row-block forward ->
+all-reduce partial sums -> all-gather row stats -> row-block backward.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU
+algorithm (the oracle's per-anchor port; /root/reference does not exist on the
+GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "supcon_fwd_bwd_sim_pairs_per_s"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--d", type=int, default=256)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--similarity", default="cosine")
+    ap.add_argument("--tau", type=float, default=0.07)
+    ap.add_argument("--lambda-uni", type=float, default=0.0)
+    ap.add_argument("--topk", type=int, default=15)
+    ap.add_argument("--alpha", type=float, default=0.0)
+    ap.add_argument("--cpu-sample-n", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=float(p["bf16_tflops"]), tflops_sustained=float(p.get("bf16_tflops_sustained", 0)),
+                    hbm_gbs=float(p["hbm_gbs"]), source="measured")
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth(n, d, dtype, seed=1337):
+    """Unit-norm embeddings + balanced binary labels, generated on the host."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, d, generator=g)
+    z = torch.nn.functional.normalize(x, dim=1).to(dtype)
+    y = torch.zeros(n, dtype=torch.int64)
+    y[torch.randperm(n, generator=g)[: n // 2]] = 1
+    return z, y
+
+
+def cpu_port_step(z, y, args):
+    """One fwd+bwd of the reference algorithm (oracle port of loss.py) on the CPU. Returns seconds."""
+    import torch
+    from oracle import supcon_oracle as O
+    zz = z.float().clone().requires_grad_(True)
+    t0 = time.perf_counter()
+    loss = O.anchor_loop_loss(zz, y, temperature=args.tau, similarity=args.similarity,
+                              uniformity_weight=args.lambda_uni, uniformity_t=2.0, topk_neg=args.topk,
+                              alpha=args.alpha)
+    loss.backward()
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = min(args.cpu_sample_n, args.n)
+    z, y = synth(n, args.d, torch.float32)
+    for _ in range(args.warmup):
+        cpu_port_step(z, y, args)
+    times = [cpu_port_step(z, y, args) for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    value = n * n / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, extra={"sample_n": n}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {n} rows/cols of the workload (N^2 pairs each step), fp32, "
+                                   f"per-anchor loop port of loss.py, torch {torch.__version__}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, extra=None):
+    cfg = {"workload": f"SupCon {args.similarity} tau={args.tau} N={args.n} d={args.d} {args.dtype} "
+                       f"fwd+bwd (BASELINE configs[3])",
+           "N": args.n, "d": args.d, "similarity": args.similarity, "tau": args.tau,
+           "lambda_uni": args.lambda_uni, "topk": args.topk, "alpha": args.alpha,
+           "parallelism": f"rows sharded over {args.gpus} rank(s)",
+           "l2_flush": "256 MiB memset between timed iterations, outside the per-step CUDA events"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from wav2vec_contr_loss_b200 import build as _build
+    _build.build()
+    from wav2vec_contr_loss_b200 import functional as Fn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    tdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    n, d = args.n, args.d
+    assert n % world == 0
+    n_local = n // world
+    z_host, y_host = synth(n, d, tdtype)
+    zl_host = z_host[rank * n_local:(rank + 1) * n_local].contiguous().pin_memory()
+    yl_host = y_host[rank * n_local:(rank + 1) * n_local].to(torch.int32).contiguous().pin_memory()
+    z_local = zl_host.to(dev)
+    y_local = yl_host.to(dev)
+    sim_id = Fn.similarity_id(args.similarity)
+    kw = dict(tau=args.tau, similarity=sim_id, lambda_uni=args.lambda_uni, uni_t=2.0, topk=args.topk,
+              alpha=args.alpha, flags=args.flags)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    launches = {"count": 0}
+
+    def step(z_loc, y_loc, timing=None):
+        """fwd + bwd through the C-ABI wrappers; returns (loss, dz_local)."""
+        if world > 1:
+            z_all = torch.empty((n, d), dtype=tdtype, device=dev)
+            y_all = torch.empty(n, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(z_all, z_loc)
+            dist.all_gather_into_tensor(y_all, y_loc)
+        else:
+            z_all, y_all = z_loc, y_loc
+        prob = Fn.make_problem(n, d, Fn._dtype_id(z_all), row_offset=rank * n_local, n_rows=n_local, **kw)
+        if timing:
+            timing[0].record()
+        stats, partials, loss = Fn.forward_rows(z_all, y_all, prob, want_loss=(world == 1))
+        if timing:
+            timing[1].record()
+        if world > 1:
+            dist.all_reduce(partials)
+            loss = Fn.finalize(prob, partials)
+            stats_all = torch.empty((n, 8), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(stats_all, stats)
+        else:
+            stats_all = stats
+        if timing:
+            timing[2].record()
+        dz = Fn.backward_rows(z_all, y_all, stats_all, partials, None, prob, out_dtype=tdtype)
+        if timing:
+            timing[3].record()
+        launches["count"] += 2 + (1 if world > 1 else 0)
+        return loss, dz
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(z_local, y_local)
+    barrier()
+
+    # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches["count"] = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s, e in ev:
+        flush.zero_()
+        s.record()
+        loss, dz = step(z_local, y_local)
+        e.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    n_launch = launches["count"]
+    ms = [s.elapsed_time(e) for s, e in ev]
+    t_local = sum(ms) / len(ms)
+    tt = torch.tensor([t_local], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tt)
+
+    # ---- end-to-end: pinned host inputs -> H2D -> fwd+bwd -> loss D2H, every step ----
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s, e in ev2:
+        flush.zero_()
+        s.record()
+        zl = zl_host.to(dev, non_blocking=True)
+        yl = yl_host.to(dev, non_blocking=True)
+        loss, dz = step(zl, yl)
+        loss_host.copy_(loss.float(), non_blocking=True)
+        e.record()
+    barrier()
+    t2 = torch.tensor([sum(s.elapsed_time(e) for s, e in ev2) / len(ev2)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2)
+
+    # ---- per-kernel durations for the roofline (events on the launching stream) ----
+    tm = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(min(args.steps, 10))]
+    for t in tm:
+        flush.zero_()
+        step(z_local, y_local, timing=t)
+    barrier()
+    fwd_ms = statistics.mean(t[0].elapsed_time(t[1]) for t in tm)
+    bwd_ms = statistics.mean(t[2].elapsed_time(t[3]) for t in tm)
+
+    if rank == 0:
+        pk = peaks()
+        pairs = float(n) * float(n)
+        flop_per_pair_bwd = (4 + (2 if args.lambda_uni > 0 else 0)) * d   # dz = (G + G^T) z  (+ W z)
+        flop_per_pair_fwd = 2 * d
+        bwd_tflops = pairs / world * flop_per_pair_bwd / (bwd_ms * 1e-3) / 1e12
+        fwd_tflops = pairs / world * flop_per_pair_fwd / (fwd_ms * 1e-3) / 1e12
+        total_tflops = pairs * (flop_per_pair_bwd + flop_per_pair_fwd) / (ms_per_step * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": pairs / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args),
+            "clocks": clocks,
+            "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(zl_host.numel() * zl_host.element_size() + yl_host.numel() * 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
+            "gpu_launches": n_launch,
+            "roofline": {"bound": "tensor", "kernel": "supcon backward (recompute S, dz = (G+G^T) z)",
+                         "achieved": bwd_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": bwd_tflops / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                         "launch_ms": bwd_ms,
+                         "algorithmic_flops_per_launch": pairs / world * flop_per_pair_bwd},
+            "roofline_fwd": {"bound": "tensor", "achieved": fwd_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
+                             "frac": fwd_tflops / pk["tflops"], "launch_ms": fwd_ms},
+            "step_tflops": total_tflops, "step_frac_of_bf16_peak": total_tflops / pk["tflops"] / world,
+            "loss": float(loss),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            ns = min(args.cpu_sample_n, n)
+            zc, yc = z_host[:ns].float(), y_host[:ns]
+            cpu_port_step(zc, yc, args)
+            tcs = [cpu_port_step(zc, yc, args) for _ in range(3)]
+            tc = statistics.median(tcs)
+            line["cpu_baseline"] = {"value": ns * ns / tc, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {ns} rows/cols of the workload, fp32, per-anchor loop port "
+                                              f"of loss.py, median of 3, {tc:.2f} s per fwd+bwd"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

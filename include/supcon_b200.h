@@ -1,0 +1,143 @@
+/*
+ * supcon_b200.h -- C ABI of the B200-native supervised-contrastive loss path.
+ *
+ * Drop-in boundary for the Stage-1 objective of JaskiratSudan/wav2vec_contr_loss:
+ * every entry point below replaces a piece of the reference's PyTorch
+ * implementation (citations are relative to the reference repository root).
+ * The reference is pure Python and has no FFI of its own; the binding a
+ * maintainer adds is the ctypes stub shown in INTEGRATION.md (shipped as
+ * wav2vec_contr_loss_b200/_cabi.py).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless it says host
+ *   - the caller owns all memory, including the workspace; the library never
+ *     allocates or frees device memory and keeps no pointer after return
+ *   - all work is issued asynchronously on `stream` (a cudaStream_t passed as
+ *     void*); no host synchronisation; CUDA-graph capturable
+ *   - return value: 0 = OK, >0 = cudaError_t, <0 = SUPCON_E_*; the message is
+ *     available from supcon_last_error() (thread-local)
+ *   - rows are "anchors"; a rank owns rows [row_offset, row_offset + n_rows) of
+ *     the N x N similarity matrix and sees all n_total columns
+ */
+#ifndef SUPCON_B200_H_
+#define SUPCON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SUPCON_ABI_VERSION 1
+
+/* element type of z / dz buffers */
+#define SUPCON_F32 0
+#define SUPCON_BF16 1
+
+/* similarity (reference loss.py:96-107) */
+#define SUPCON_COSINE 0
+#define SUPCON_GEODESIC 1
+
+/* problem.flags */
+#define SUPCON_FLAG_FORCE_EXACT 1u   /* never take the bf16 tensor-core path          */
+#define SUPCON_FLAG_FORCE_TENSOR 2u  /* fail (SUPCON_E_UNSUPPORTED) instead of falling back */
+#define SUPCON_FLAG_NO_SMALL 4u      /* do not use the single-launch small-batch kernel */
+
+/* error codes */
+#define SUPCON_E_INVALID (-1)
+#define SUPCON_E_UNSUPPORTED (-2)
+#define SUPCON_E_WORKSPACE (-3)
+
+/* per-row statistics written by the forward pass and consumed by the backward
+ * pass: SUPCON_STATS_STRIDE 32-bit words per row, row-major. */
+#define SUPCON_STATS_STRIDE 8
+#define SUPCON_ST_LSE 0      /* f32  log sum_{j!=i} exp(s_ij/tau)                    */
+#define SUPCON_ST_LSE_M 1    /* f32  same over positives + selected hard negatives   */
+#define SUPCON_ST_NPOS 2     /* i32  |pos_i|                                         */
+#define SUPCON_ST_NNEG 3     /* i32  |neg_i|                                         */
+#define SUPCON_ST_THR_VAL 4  /* f32  similarity of the lowest-ranked selected negative
+                                     (-inf when every negative is selected)          */
+#define SUPCON_ST_THR_IDX 5  /* i32  its column index (INT32_MAX when all selected)  */
+#define SUPCON_ST_WSUM 6     /* f32  sum_{j!=i} exp(-t |z_i - z_j|^2)                */
+#define SUPCON_ST_POS_MEAN 7 /* f32  mean_{p in pos_i} s_ip/tau                      */
+
+/* partial sums exchanged between ranks (doubles) */
+#define SUPCON_N_PARTIALS 8
+#define SUPCON_P_SUM_FULL 0
+#define SUPCON_P_CNT_FULL 1
+#define SUPCON_P_SUM_MINED 2
+#define SUPCON_P_CNT_MINED 3
+#define SUPCON_P_SUM_W 4
+
+typedef struct supcon_problem {
+  int32_t n_total;    /* N: columns = global batch                                   */
+  int32_t row_offset; /* first owned row                                             */
+  int32_t n_rows;     /* owned rows                                                  */
+  int32_t d;          /* embedding width                                             */
+  int32_t z_dtype;    /* SUPCON_F32 | SUPCON_BF16                                    */
+  int32_t similarity; /* SUPCON_COSINE | SUPCON_GEODESIC   (loss.py:21,30-32)        */
+  int32_t topk;       /* topk_neg                           (loss.py:113)            */
+  uint32_t flags;
+  float tau;          /* temperature                        (loss.py:20,28)          */
+  float alpha;        /* blend of full and mined loss       (loss.py:114,146)        */
+  float lambda_uni;   /* uniformity_weight                  (loss.py:23,149-151)     */
+  float uni_t;        /* uniformity_t                       (loss.py:24,93)          */
+} supcon_problem_t;
+
+int supcon_abi_version(void);
+const char* supcon_last_error(void);
+
+/* Bytes of scratch the calls below need for this problem (host out-param). */
+int supcon_workspace_bytes(const supcon_problem_t* p, size_t* bytes_out);
+
+/* Forward over the owned rows.  Replaces the similarity Gram, masks, the
+ * per-anchor loop and the uniformity row sums: loss.py:96-107, :116-135, :77-93.
+ *   z_all      [n_total][d]   labels_all [n_total] int32
+ *   row_stats  [n_rows][SUPCON_STATS_STRIDE]      (out)
+ *   partials   [SUPCON_N_PARTIALS] doubles         (out; this rank's sums)
+ *   loss_out   optional; only when the rank owns every row: the scalar loss
+ *              (loss.py:137-153) is written by the same launch */
+int supcon_forward_rows(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                        float* row_stats, double* partials, float* loss_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Scalar loss from globally summed partials (alpha blend, empty-set fall-backs,
+ * uniformity term): loss.py:137-153. */
+int supcon_finalize(const supcon_problem_t* p, const double* partials_global, float* loss_out,
+                    void* stream);
+
+/* Backward for the owned rows (replaces autograd through loss.py:96-153):
+ *   dz_i = grad_out * sum_j (G_ij + G_ji) z_j (+ uniformity), recomputing the
+ *   similarity tiles; needs the statistics of ALL rows and the global partials.
+ *   stats_all  [n_total][SUPCON_STATS_STRIDE]
+ *   grad_out   device scalar (NULL = 1.0)
+ *   dz_out     [n_rows][d] in dz_dtype */
+int supcon_backward_rows(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                         const float* stats_all, const double* partials_global,
+                         const float* grad_out, void* dz_out, int32_t dz_dtype, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* Whole batch on one GPU: loss and (if dz_out != NULL) d loss / d z in as few
+ * launches as the shape allows (one for small batches).  row_stats/partials
+ * are scratch outputs as above. */
+int supcon_loss_and_grad(const supcon_problem_t* p, const void* z, const int32_t* labels,
+                         float* loss_out, void* dz_out, int32_t dz_dtype, float* row_stats,
+                         double* partials, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Row L2 normalisation either side of the loss (stage1_utils.py:123,149):
+ *   z = x / max(|x|, 1e-12);   dx = (dz - z (z.dz)) / max(|x|, 1e-12) */
+int supcon_normalize_forward(const float* x, int32_t n, int32_t d, void* z_out, int32_t z_dtype,
+                             float* norms_out, void* stream);
+int supcon_normalize_backward(const void* z, int32_t z_dtype, const float* norms, const void* dz,
+                              int32_t dz_dtype, int32_t n, int32_t d, float* dx_out, void* stream);
+
+/* Diagnostics used by the parity tests: hard-negative index sets of the owned
+ * rows, recomputed from the statistics (index ascending, -1 padded). */
+int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                        const float* row_stats, int32_t* idx_out /*[n_rows][topk]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUPCON_B200_H_ */

@@ -1,0 +1,252 @@
+"""GPU: the CUDA path (through the C-ABI) against the oracle and the committed
+reference outputs.  Tolerances (north_star): loss and dz within 1e-5 relative
+on the fp32 path, 2e-3 on the bf16-input path; hard-negative index sets exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden_names, load_golden
+from oracle import supcon_oracle as O
+import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5      # north_star: fp32 / tf32-off path
+TOL_BF16 = 2e-3     # north_star: bf16 input, fp32 accumulate
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fixtures_fp32(cuda_device, name):
+    meta, g = load_golden(name)
+    z, y = torch.from_numpy(g["z"]), torch.from_numpy(g["labels"])
+    kw = dict(tau=meta["tau"], similarity=meta["similarity"], lam=meta["lambda_uni"], t=meta["uni_t"],
+              topk=meta["topk"], alpha=meta["alpha"])
+    loss, dz = G.kernel_loss_and_grad(z, y, **kw)
+    assert loss == pytest.approx(float(g["loss64"]), rel=TOL_F32, abs=1e-6)
+    assert loss == pytest.approx(float(g["loss32"]), rel=TOL_F32, abs=1e-6)
+    if meta["n"] < 2:
+        return
+    ref64 = torch.from_numpy(g["dz64"])
+    if meta["kind"] == "ties":      # reference tie order is unspecified: use the lowest-index oracle
+        ref64 = G.oracle_for(z, y, **kw)["dz"]
+    if float(ref64.norm()) == 0.0:
+        assert float(dz.norm()) == 0.0
+    else:
+        assert G.rel_err(dz, ref64) < TOL_F32
+
+
+CASES = [
+    # n, d, kind, classes, sim, tau, lam, t, K, alpha
+    (64, 256, "iso", 2, "cosine", 0.07, 0.0, 2.0, 15, 0.0),          # C1
+    (64, 256, "iso", 2, "geodesic", 0.07, 0.05, 2.0, 15, 0.0),       # C2
+    (1024, 256, "iso", 2, "cosine", 0.07, 0.0, 2.0, 15, 0.0),        # C3 alpha schedule
+    (1024, 256, "iso", 2, "cosine", 0.07, 0.0, 2.0, 15, 0.0125),
+    (1024, 256, "iso", 2, "cosine", 0.07, 0.0, 2.0, 15, 0.5),
+    (1024, 256, "iso", 2, "cosine", 0.07, 0.0, 2.0, 15, 1.0),
+    (1024, 256, "clustered", 2, "cosine", 0.07, 0.0, 2.0, 32, 0.5),
+    (1024, 256, "iso", 2, "cosine", 0.07, 0.0, 2.0, 600, 1.0),       # K >= N/2: all negatives
+    (1000, 200, "iso", 5, "geodesic", 0.1, 0.2, 2.0, 15, 0.37),      # ragged N, d; multi-class
+    (257, 48, "clustered", 3, "geodesic", 0.2, 0.1, 3.0, 8, 1.0),
+    (130, 19, "iso", 7, "cosine", 0.07, 0.1, 2.0, 32, 0.37),         # odd d -> scalar loads
+    (2, 4, "iso", 1, "cosine", 0.5, 0.5, 2.0, 3, 0.5),
+    (3, 5, "iso", 2, "geodesic", 0.5, 0.5, 2.0, 3, 0.5),
+]
+
+
+@pytest.mark.parametrize("n,d,kind,classes,sim,tau,lam,t,k,alpha", CASES)
+def test_seeded_cases_fp32(cuda_device, n, d, kind, classes, sim, tau, lam, t, k, alpha):
+    x, y = O.make_inputs(n, d, kind, classes=max(classes, 2))
+    if classes == 1:
+        y = torch.zeros_like(y)
+    z = F.normalize(x, dim=1)
+    kw = dict(tau=tau, similarity=sim, lam=lam, t=t, topk=k, alpha=alpha)
+    loss, dz = G.kernel_loss_and_grad(z, y, **kw)
+    ref = G.oracle_for(z, y, **kw)
+    assert loss == pytest.approx(ref["loss"], rel=TOL_F32, abs=1e-6)
+    assert G.rel_err(dz, ref["dz"]) < TOL_F32
+
+
+@pytest.mark.parametrize("sim", ["cosine", "geodesic"])
+def test_bf16_inputs(cuda_device, sim):
+    x, y = O.make_inputs(512, 256, "iso")
+    zb = F.normalize(x, dim=1).to(torch.bfloat16)
+    kw = dict(tau=0.07, similarity=sim, lam=0.05, topk=15, alpha=0.5)
+    loss, dz = G.kernel_loss_and_grad(zb, y, dtype=torch.bfloat16, **kw)
+    ref = G.oracle_for(zb.float(), y, **kw)      # oracle semantics for bf16: loss.py on z_bf16.float()
+    assert loss == pytest.approx(ref["loss"], rel=TOL_BF16)
+    assert G.rel_err(dz, ref["dz"]) < 2 * TOL_BF16     # dz itself is rounded to bf16 on return
+
+
+def _exact_arith_inputs(n, d, seed):
+    """Entries in {0, +-1/2, +-1/4}: every dot product is exact in fp32 and fp64,
+    so hard-negative sets (with their many exact ties) must match bit-for-bit."""
+    g = torch.Generator().manual_seed(seed)
+    vals = torch.tensor([0.0, 0.5, -0.5, 0.25, -0.25])
+    z = vals[torch.randint(0, 5, (n, d), generator=g)]
+    y = torch.randint(0, 3, (n,), generator=g)
+    return z, y
+
+
+@pytest.mark.parametrize("n,d,k", [(96, 8, 7), (300, 12, 15), (1024, 16, 32)])
+def test_hard_negative_index_sets_exact(cuda_device, n, d, k):
+    z, y = _exact_arith_inputs(n, d, seed=n)
+    out = G.kernel_stats(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0)
+    ref = G.oracle_for(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0, want_topk_idx=True, want_grad=False)
+    got = out["idx"].cpu().tolist()
+    for i in range(n):
+        mine = [j for j in got[i] if j >= 0]
+        assert mine == sorted(ref["stats"]["topk_idx"][i]), f"row {i}"
+    # and the gradient that depends on those sets
+    loss, dz = G.kernel_loss_and_grad(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0)
+    full = G.oracle_for(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0)
+    assert loss == pytest.approx(full["loss"], rel=TOL_F32)
+    assert G.rel_err(dz, full["dz"]) < TOL_F32
+
+
+def test_appendix_b_tie_case(cuda_device):
+    z = F.normalize(torch.tensor([[1, 0], [1, 0], [0, 1], [0, 1], [0, 1], [.6, .8]]), dim=1)
+    y = torch.tensor([1, 1, 0, 0, 0, 0])
+    loss, dz = G.kernel_loss_and_grad(z, y, tau=0.5, similarity="cosine", topk=2, alpha=1.0)
+    assert loss == pytest.approx(1.0041676759719849, rel=TOL_F32)
+    out = G.kernel_stats(z, y, tau=0.5, similarity="cosine", topk=2, alpha=1.0)
+    assert out["idx"][0].tolist() == [2, 5] and out["idx"][1].tolist() == [2, 5]
+
+
+def test_analytic_known_answers(cuda_device):
+    y = torch.tensor([1, 0] * 32)
+    z = torch.ones(64, 8) / math.sqrt(8.0)
+    for sim in ("cosine", "geodesic"):
+        loss, _ = G.kernel_loss_and_grad(z, y, tau=0.07, similarity=sim, topk=15, alpha=0.0)
+        assert loss == pytest.approx(math.log(63.0), rel=TOL_F32)
+        loss, _ = G.kernel_loss_and_grad(z, y, tau=0.07, similarity=sim, topk=15, alpha=1.0)
+        assert loss == pytest.approx(math.log(46.0), rel=TOL_F32)
+    z = torch.eye(256)[:64]
+    loss, _ = G.kernel_loss_and_grad(z, y, tau=0.07, similarity="cosine", lam=0.05, t=2.0)
+    assert loss == pytest.approx(3.9431347536906003, rel=TOL_F32)
+
+
+def test_unnormalised_and_small_temperature(cuda_device):
+    """z is taken as given: large logits must not overflow (online max)."""
+    x, y = O.make_inputs(200, 32, "iso", seed=5)
+    z = 3.0 * F.normalize(x, dim=1)
+    for tau in (0.07, 0.01):
+        kw = dict(tau=tau, similarity="cosine", lam=0.0, topk=5, alpha=0.5)
+        loss, dz = G.kernel_loss_and_grad(z, y, **kw)
+        ref = G.oracle_for(z, y, **kw)
+        assert math.isfinite(loss)
+        assert loss == pytest.approx(ref["loss"], rel=TOL_F32)
+        assert G.rel_err(dz, ref["dz"]) < 5 * TOL_F32   # logits ~ 9/tau: conditioning, SURVEY H7
+
+
+def test_autograd_contract(cuda_device):
+    from wav2vec_contr_loss_b200 import SupConBinaryLoss, SupConMultiClassLoss
+    x, y = O.make_inputs(64, 32, "iso", classes=4)
+    x = x.to(cuda_device).requires_grad_(True)
+    z = F.normalize(x, p=2, dim=1)
+    mod = SupConBinaryLoss(0.07, "cosine")
+    loss = mod(z, y.to(cuda_device), topk_neg=15, alpha=0.0)
+    assert loss.dim() == 0 and loss.dtype == torch.float32 and loss.device == z.device
+    (2.5 * loss).backward()
+    ref = G.oracle_for(F.normalize(x.detach().cpu(), dim=1), y, tau=0.07, similarity="cosine", topk=15)
+    zz, nrm = O.normalize_fwd(x.detach().cpu().double())
+    dx = O.normalize_bwd(zz, nrm, ref["dz"]) * 2.5
+    assert G.rel_err(x.grad.cpu(), dx) < TOL_F32
+    # forward-only under no_grad: no graph, same value
+    with torch.no_grad():
+        l2 = mod(z, y.to(cuda_device), topk_neg=15, alpha=0.0)
+    assert not l2.requires_grad and float(l2) == float(loss)
+    # multi-class class == binary class with cosine, alpha = 0
+    l3 = SupConMultiClassLoss(0.07)(z.detach(), y.to(cuda_device))
+    assert float(l3) == pytest.approx(float(loss), rel=1e-6)
+    # float labels and (B,1) labels are accepted (loss.py:123)
+    l4 = mod(z.detach(), y.to(cuda_device).float().view(-1, 1) * 0.5)
+    assert float(l4) == pytest.approx(float(loss), rel=1e-6)
+
+
+def test_multiclass_fixture(cuda_device):
+    import os
+    from conftest import GOLDEN
+    from wav2vec_contr_loss_b200 import SupConMultiClassLoss
+    f = np.load(os.path.join(GOLDEN, "multiclass_n64_d32.npz"))
+    z = torch.from_numpy(f["z"]).to(cuda_device).requires_grad_(True)
+    loss = SupConMultiClassLoss(0.1)(z, torch.from_numpy(f["labels"]).to(cuda_device))
+    loss.backward()
+    assert float(loss) == pytest.approx(float(f["loss64"]), rel=TOL_F32)
+    assert G.rel_err(z.grad.cpu(), torch.from_numpy(f["dz64"])) < TOL_F32
+
+
+def test_row_blocks_compose(cuda_device):
+    """Two row blocks through the C-ABI == whole batch (multi-rank contract)."""
+    from wav2vec_contr_loss_b200 import functional as Fn
+    x, y = O.make_inputs(200, 64, "clustered", classes=3)
+    z = F.normalize(x, dim=1)
+    kw = dict(tau=0.1, similarity="geodesic", lam=0.1, t=2.0, topk=5, alpha=0.3)
+    a = G.kernel_stats(z, y, row_offset=0, n_rows=120, **kw)
+    b = G.kernel_stats(z, y, row_offset=120, n_rows=80, **kw)
+    partials = a["partials"] + b["partials"]
+    stats = torch.cat([a["stats"], b["stats"]])
+    whole_prob = Fn.make_problem(200, 64, 0, tau=0.1, similarity=1, lambda_uni=0.1, uni_t=2.0, topk=5, alpha=0.3)
+    loss = float(Fn.finalize(whole_prob, partials))
+    ref = G.oracle_for(z, y, **kw)
+    assert loss == pytest.approx(ref["loss"], rel=TOL_F32)
+    dz_b = Fn.backward_rows(b["z"], b["y"], stats, partials, None, b["prob"])
+    assert G.rel_err(dz_b.cpu(), ref["dz"][120:]) < TOL_F32
+
+
+def test_normalize_kernels(cuda_device):
+    from wav2vec_contr_loss_b200 import l2_normalize
+    x = torch.randn(300, 256, generator=torch.Generator().manual_seed(0))
+    x[5] = 0.0
+    xg = x.to(cuda_device).requires_grad_(True)
+    z = l2_normalize(xg)
+    w = torch.randn(300, 256, generator=torch.Generator().manual_seed(1))
+    (z * w.to(cuda_device)).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    zr = F.normalize(xr, p=2, dim=1)
+    (zr * w).sum().backward()
+    assert torch.allclose(z.cpu(), zr, rtol=2e-6, atol=1e-7)
+    assert torch.allclose(xg.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_large_batch_properties_fp32(cuda_device):
+    """N = 4096: against the row-blocked fp64 oracle, plus size-independent
+    properties (sum_i dz_i . z_i relation is not available; use: gradient of a
+    label-permuted/row-permuted batch is the permuted gradient)."""
+    x, y = O.make_inputs(4096, 256, "iso")
+    z = F.normalize(x, dim=1)
+    kw = dict(tau=0.07, similarity="cosine", lam=0.0, topk=15, alpha=0.5)
+    loss, dz = G.kernel_loss_and_grad(z, y, **kw)
+    ref = G.oracle_for(z, y, **kw)
+    assert loss == pytest.approx(ref["loss"], rel=TOL_F32)
+    assert G.rel_err(dz, ref["dz"]) < TOL_F32
+    perm = torch.randperm(4096, generator=torch.Generator().manual_seed(9))
+    loss_p, dz_p = G.kernel_loss_and_grad(z[perm], y[perm], **kw)
+    assert loss_p == pytest.approx(loss, rel=1e-6)
+    assert G.rel_err(dz_p, dz[perm]) < 1e-5
+
+
+def test_training_step_reduces_loss(cuda_device):
+    """The caller's shape (stage1_utils.py:122-130): head -> mean -> normalize -> loss -> backward -> step."""
+    from wav2vec_contr_loss_b200 import SupConBinaryLoss
+    torch.manual_seed(0)
+    head = torch.nn.Linear(64, 32).to(cuda_device)
+    opt = torch.optim.AdamW(head.parameters(), lr=1e-2)
+    loss_fn = SupConBinaryLoss(temperature=0.07, similarity="geodesic", uniformity_weight=0.05)
+    feats = torch.randn(64, 64, 10, device=cuda_device)
+    labels = (torch.arange(64, device=cuda_device) % 2).long()
+    feats[labels == 1, :8] += 1.0
+    first = last = None
+    for step in range(30):
+        seq = head(feats.transpose(1, 2)).transpose(1, 2)
+        z = F.normalize(seq.mean(dim=-1), p=2, dim=1)
+        loss = loss_fn(z, labels, topk_neg=15, alpha=0.3)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(head.parameters(), 5.0)
+        opt.step()
+        first = float(loss) if first is None else first
+        last = float(loss)
+    assert last < first - 0.05

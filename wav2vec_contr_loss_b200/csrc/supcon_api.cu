@@ -1,0 +1,247 @@
+// C-ABI dispatcher of libsupcon_b200.so (see include/supcon_b200.h).
+//
+// Routes each call to one of the kernel families:
+//   small  single-launch cluster kernel for small batches   (supcon_small.cu)
+//   tc     bf16 tcgen05/TMEM/TMA flash-style kernels         (supcon_tc.cu)
+//   ffma   exact fp32 CUDA-core kernels, any shape           (supcon_ffma.cu)
+// There is no CPU path: if no CUDA kernel can take the problem the call fails.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "supcon_common.cuh"
+#include "supcon_internal.h"
+
+namespace supcon {
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (int)e;
+}
+
+int validate(const supcon_problem_t* p) {
+  if (!p) return fail(SUPCON_E_INVALID, "problem is NULL");
+  if (p->n_total < 2) return fail(SUPCON_E_INVALID, "n_total must be >= 2 (got %d)", p->n_total);
+  if (p->d < 1) return fail(SUPCON_E_INVALID, "d must be >= 1 (got %d)", p->d);
+  if (p->n_rows < 1 || p->row_offset < 0 || p->row_offset + p->n_rows > p->n_total)
+    return fail(SUPCON_E_INVALID, "row block [%d, %d) outside [0, %d)", p->row_offset,
+                p->row_offset + p->n_rows, p->n_total);
+  if (p->z_dtype != SUPCON_F32 && p->z_dtype != SUPCON_BF16)
+    return fail(SUPCON_E_INVALID, "unknown z_dtype %d", p->z_dtype);
+  if (p->similarity != SUPCON_COSINE && p->similarity != SUPCON_GEODESIC)
+    return fail(SUPCON_E_INVALID, "Unknown similarity: %d", p->similarity);
+  if (!(p->tau > 0.f)) return fail(SUPCON_E_INVALID, "tau must be > 0");
+  return 0;
+}
+
+bool needs_mining(const supcon_problem_t* p) { return p->alpha != 0.f && p->topk >= 1; }
+
+bool vec_ok(const void* z, const supcon_problem_t* p) {
+  size_t al = p->z_dtype == SUPCON_BF16 ? 8 : 16;
+  return (p->d % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) % al) == 0);
+}
+
+FfmaArgs make_ffma(const supcon_problem_t* p, const void* z, const int32_t* labels, void* ws) {
+  FfmaArgs a;
+  memset(&a, 0, sizeof(a));
+  a.z = z; a.labels = labels;
+  a.ticket = reinterpret_cast<unsigned*>(ws);
+  a.block_partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
+  a.n_total = p->n_total; a.row_offset = p->row_offset; a.n_rows = p->n_rows; a.d = p->d;
+  a.z_dtype = p->z_dtype; a.similarity = p->similarity; a.topk = p->topk < 0 ? 0 : p->topk;
+  a.mine = needs_mining(p) ? 1 : 0;
+  int cap = ffma_kcap();
+  a.kcap = a.mine ? (a.topk < cap ? a.topk : cap) : 0;
+  a.vec_ok = vec_ok(z, p) ? 1 : 0;
+  a.tau = p->tau; a.alpha = p->alpha; a.lambda_uni = p->lambda_uni; a.uni_t = p->uni_t;
+  return a;
+}
+
+__global__ void finalize_kernel(const double* pg, float* loss_out, int n_total, float tau, float alpha,
+                                float lambda_uni, float uni_t) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    *loss_out = global_coef(pg, n_total, tau, alpha, lambda_uni, uni_t).loss;
+}
+
+// ---- row L2 normalisation (stage1_utils.py:123,149): one warp per row ----
+template <typename TO>
+__global__ void normalize_fwd_kernel(const float* __restrict__ x, int n, int d, TO* __restrict__ z,
+                                     float* __restrict__ norms) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + (int64_t)row * d;
+  float s = 0.f;
+  for (int k = lane; k < d; k += 32) { float v = __ldg(xr + k); s = fmaf(v, v, s); }
+  s = warp_sum(s);
+  float nrm = fmaxf(sqrtf(s), 1e-12f);
+  if (lane == 0 && norms) norms[row] = nrm;
+  for (int k = lane; k < d; k += 32) {
+    float v = __fdiv_rn(__ldg(xr + k), nrm);
+    if constexpr (sizeof(TO) == 4) z[(int64_t)row * d + k] = v;
+    else z[(int64_t)row * d + k] = __float2bfloat16(v);
+  }
+}
+
+template <typename TZ, typename TG>
+__global__ void normalize_bwd_kernel(const TZ* __restrict__ z, const float* __restrict__ norms,
+                                     const TG* __restrict__ dz, int n, int d, float* __restrict__ dx) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const TZ* zr = z + (int64_t)row * d;
+  const TG* gr = dz + (int64_t)row * d;
+  float s = 0.f;
+  for (int k = lane; k < d; k += 32) s = fmaf(ld_elem<TZ>(zr + k), ld_elem<TG>(gr + k), s);
+  s = warp_sum(s);
+  float inv = __fdiv_rn(1.0f, norms[row]);
+  for (int k = lane; k < d; k += 32)
+    dx[(int64_t)row * d + k] = (ld_elem<TG>(gr + k) - ld_elem<TZ>(zr + k) * s) * inv;
+}
+
+}  // namespace
+}  // namespace supcon
+
+using namespace supcon;
+
+extern "C" {
+
+int supcon_abi_version(void) { return SUPCON_ABI_VERSION; }
+const char* supcon_last_error(void) { return g_err.c_str(); }
+
+int supcon_workspace_bytes(const supcon_problem_t* p, size_t* bytes_out) {
+  if (int rc = validate(p)) return rc;
+  if (!bytes_out) return fail(SUPCON_E_INVALID, "bytes_out is NULL");
+  *bytes_out = ffma_workspace_bytes(p->n_rows);
+  return 0;
+}
+
+int supcon_forward_rows(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                        float* row_stats, double* partials, float* loss_out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!z_all || !labels_all || !row_stats || !partials || !workspace)
+    return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_forward_rows");
+  if (workspace_bytes < ffma_workspace_bytes(p->n_rows))
+    return fail(SUPCON_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes,
+                ffma_workspace_bytes(p->n_rows));
+  if (loss_out && (p->row_offset != 0 || p->n_rows != p->n_total))
+    return fail(SUPCON_E_INVALID, "loss_out needs a rank that owns every row; use supcon_finalize");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+  FfmaArgs a = make_ffma(p, z_all, labels_all, workspace);
+  a.row_stats = row_stats; a.partials = partials; a.loss_out = loss_out;
+  e = ffma_forward(a, st);
+  if (e != cudaSuccess) return cuda_fail(e, "ffma_forward");
+  return 0;
+}
+
+int supcon_finalize(const supcon_problem_t* p, const double* partials_global, float* loss_out,
+                    void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!partials_global || !loss_out) return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_finalize");
+  finalize_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partials_global, loss_out, p->n_total, p->tau, p->alpha, p->lambda_uni, p->uni_t);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "finalize_kernel");
+  return 0;
+}
+
+int supcon_backward_rows(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                         const float* stats_all, const double* partials_global, const float* grad_out,
+                         void* dz_out, int32_t dz_dtype, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!z_all || !labels_all || !stats_all || !partials_global || !dz_out)
+    return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_backward_rows");
+  if (dz_dtype != SUPCON_F32 && dz_dtype != SUPCON_BF16)
+    return fail(SUPCON_E_INVALID, "unknown dz_dtype %d", dz_dtype);
+  (void)workspace_bytes;
+  FfmaArgs a = make_ffma(p, z_all, labels_all, workspace ? workspace : (void*)dz_out);
+  a.stats_all = stats_all;
+  a.partials = const_cast<double*>(partials_global);
+  a.grad_out = grad_out; a.dz_out = dz_out;
+  cudaError_t e = ffma_backward(a, dz_dtype, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ffma_backward");
+  return 0;
+}
+
+int supcon_loss_and_grad(const supcon_problem_t* p, const void* z, const int32_t* labels, float* loss_out,
+                         void* dz_out, int32_t dz_dtype, float* row_stats, double* partials,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (p->row_offset != 0 || p->n_rows != p->n_total)
+    return fail(SUPCON_E_INVALID, "supcon_loss_and_grad needs the whole batch on one rank");
+  if (!loss_out) return fail(SUPCON_E_INVALID, "loss_out is NULL");
+  int rc = supcon_forward_rows(p, z, labels, row_stats, partials, loss_out, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  if (dz_out)
+    rc = supcon_backward_rows(p, z, labels, row_stats, partials, nullptr, dz_out, dz_dtype, workspace,
+                              workspace_bytes, stream);
+  return rc;
+}
+
+int supcon_normalize_forward(const float* x, int32_t n, int32_t d, void* z_out, int32_t z_dtype,
+                             float* norms_out, void* stream) {
+  if (!x || !z_out || n < 1 || d < 1) return fail(SUPCON_E_INVALID, "bad arguments to supcon_normalize_forward");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int wpb = 8, blocks = (n + wpb - 1) / wpb;
+  if (z_dtype == SUPCON_BF16)
+    normalize_fwd_kernel<__nv_bfloat16><<<blocks, wpb * 32, 0, st>>>(x, n, d, (__nv_bfloat16*)z_out, norms_out);
+  else if (z_dtype == SUPCON_F32)
+    normalize_fwd_kernel<float><<<blocks, wpb * 32, 0, st>>>(x, n, d, (float*)z_out, norms_out);
+  else return fail(SUPCON_E_INVALID, "unknown z_dtype %d", z_dtype);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "normalize_fwd_kernel");
+  return 0;
+}
+
+int supcon_normalize_backward(const void* z, int32_t z_dtype, const float* norms, const void* dz,
+                              int32_t dz_dtype, int32_t n, int32_t d, float* dx_out, void* stream) {
+  if (!z || !norms || !dz || !dx_out || n < 1 || d < 1)
+    return fail(SUPCON_E_INVALID, "bad arguments to supcon_normalize_backward");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int wpb = 8, blocks = (n + wpb - 1) / wpb;
+  typedef __nv_bfloat16 bf;
+  if (z_dtype == SUPCON_F32 && dz_dtype == SUPCON_F32)
+    normalize_bwd_kernel<float, float><<<blocks, wpb * 32, 0, st>>>((const float*)z, norms, (const float*)dz, n, d, dx_out);
+  else if (z_dtype == SUPCON_BF16 && dz_dtype == SUPCON_F32)
+    normalize_bwd_kernel<bf, float><<<blocks, wpb * 32, 0, st>>>((const bf*)z, norms, (const float*)dz, n, d, dx_out);
+  else if (z_dtype == SUPCON_F32 && dz_dtype == SUPCON_BF16)
+    normalize_bwd_kernel<float, bf><<<blocks, wpb * 32, 0, st>>>((const float*)z, norms, (const bf*)dz, n, d, dx_out);
+  else if (z_dtype == SUPCON_BF16 && dz_dtype == SUPCON_BF16)
+    normalize_bwd_kernel<bf, bf><<<blocks, wpb * 32, 0, st>>>((const bf*)z, norms, (const bf*)dz, n, d, dx_out);
+  else return fail(SUPCON_E_INVALID, "unknown dtype");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "normalize_bwd_kernel");
+  return 0;
+}
+
+int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                        const float* row_stats, int32_t* idx_out, void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!z_all || !labels_all || !row_stats || !idx_out || p->topk < 1)
+    return fail(SUPCON_E_INVALID, "bad arguments to supcon_topk_indices");
+  FfmaArgs a = make_ffma(p, z_all, labels_all, (void*)idx_out);
+  a.row_stats = const_cast<float*>(row_stats);
+  cudaError_t e = ffma_topk_indices(a, idx_out, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ffma_topk_indices");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+"""Torch-facing wrappers around the C-ABI: tensors in, tensors out.
+
+PyTorch is plumbing here (device memory, streams, autograd hook-up).  Every
+number is produced by libsupcon_b200.so; there is no eager/CPU fallback and a
+non-CUDA tensor is rejected.
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+_SIM = {"cosine": _cabi.COSINE, "geodesic": _cabi.GEODESIC}
+
+
+def similarity_id(similarity: str) -> int:
+    key = similarity.lower()
+    if key not in _SIM:
+        # same text as reference loss.py:32
+        raise ValueError(f"Unknown similarity: {similarity}")
+    return _SIM[key]
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _dtype_id(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _cabi.F32
+    if t.dtype == torch.bfloat16:
+        return _cabi.BF16
+    raise TypeError(f"unsupported element type {t.dtype}")
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} must be a CUDA tensor: the B200 SupCon path has no CPU fallback "
+            f"(got device {t.device})")
+
+
+def canonical_z(z: torch.Tensor) -> torch.Tensor:
+    """Contiguous fp32 or bf16 view/copy of the embeddings."""
+    if z.dim() != 2:
+        raise ValueError(f"z must be (B, D), got shape {tuple(z.shape)}")
+    if z.dtype not in (torch.float32, torch.bfloat16):
+        z = z.float()
+    return z.contiguous()
+
+
+def canonical_labels(labels: torch.Tensor, n: int) -> torch.Tensor:
+    """int32 class keys: equal labels <-> equal keys (reference compares with ==,
+    loss.py:123-124; any dtype, shape (B,) or (B,1))."""
+    lab = labels.reshape(-1)
+    if lab.numel() != n:
+        raise ValueError(f"labels must have {n} elements, got {lab.numel()}")
+    if lab.is_floating_point():
+        lab = (lab.float() + 0.0).contiguous().view(torch.int32)   # -0.0 -> +0.0, then bit pattern
+    else:
+        lab = lab.to(torch.int32)
+    return lab.contiguous()
+
+
+def make_problem(n_total, d, z_dtype_id, *, tau, similarity, lambda_uni=0.0, uni_t=2.0, topk=32,
+                 alpha=0.0, row_offset=0, n_rows=None, flags=0) -> _cabi.Problem:
+    topk = max(0, min(int(topk), 2**31 - 1))
+    return _cabi.Problem(
+        n_total=int(n_total), row_offset=int(row_offset),
+        n_rows=int(n_total if n_rows is None else n_rows), d=int(d), z_dtype=int(z_dtype_id),
+        similarity=int(similarity), topk=topk, flags=int(flags), tau=float(tau), alpha=float(alpha),
+        lambda_uni=float(lambda_uni), uni_t=float(uni_t))
+
+
+def workspace_for(prob: _cabi.Problem, device) -> torch.Tensor:
+    lib = _cabi.load()
+    nbytes = ctypes.c_size_t(0)
+    _cabi.check(lib.supcon_workspace_bytes(ctypes.byref(prob), ctypes.byref(nbytes)), "supcon_workspace_bytes")
+    return torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=device)
+
+
+def forward_rows(z_all: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Problem, want_loss: bool):
+    """Row-block forward. Returns (row_stats [n_rows,8] f32, partials [8] f64, loss or None)."""
+    _require_cuda(z_all, "z")
+    lib = _cabi.load()
+    dev = z_all.device
+    with torch.cuda.device(dev):
+        stats = torch.empty((prob.n_rows, _cabi.STATS_STRIDE), dtype=torch.float32, device=dev)
+        partials = torch.empty(_cabi.N_PARTIALS, dtype=torch.float64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev) if want_loss else None
+        ws = workspace_for(prob, dev)
+        _cabi.check(lib.supcon_forward_rows(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(stats),
+                                            _p(partials), _p(loss), _p(ws), ws.numel(), _stream(dev)),
+                    "supcon_forward_rows")
+    return stats, partials, loss
+
+
+def finalize(prob: _cabi.Problem, partials_global: torch.Tensor) -> torch.Tensor:
+    lib = _cabi.load()
+    dev = partials_global.device
+    with torch.cuda.device(dev):
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        _cabi.check(lib.supcon_finalize(ctypes.byref(prob), _p(partials_global), _p(loss), _stream(dev)),
+                    "supcon_finalize")
+    return loss
+
+
+def backward_rows(z_all, labels_i32, stats_all, partials_global, grad_out, prob: _cabi.Problem,
+                  out_dtype=torch.float32) -> torch.Tensor:
+    lib = _cabi.load()
+    dev = z_all.device
+    with torch.cuda.device(dev):
+        dz = torch.empty((prob.n_rows, prob.d), dtype=out_dtype, device=dev)
+        ws = workspace_for(prob, dev)
+        g = None
+        if grad_out is not None:
+            g = grad_out.detach().reshape(()).to(device=dev, dtype=torch.float32)
+        _cabi.check(lib.supcon_backward_rows(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(stats_all),
+                                             _p(partials_global), _p(g), _p(dz), _dtype_id(dz), _p(ws),
+                                             ws.numel(), _stream(dev)),
+                    "supcon_backward_rows")
+    return dz
+
+
+def topk_indices(z_all, labels_i32, row_stats, prob: _cabi.Problem) -> torch.Tensor:
+    lib = _cabi.load()
+    dev = z_all.device
+    with torch.cuda.device(dev):
+        idx = torch.empty((prob.n_rows, prob.topk), dtype=torch.int32, device=dev)
+        _cabi.check(lib.supcon_topk_indices(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(row_stats),
+                                            _p(idx), _stream(dev)), "supcon_topk_indices")
+    return idx
+
+
+def _loss_dtype(loss: torch.Tensor, z_dtype) -> torch.Tensor:
+    """The reference returns the loss in z's dtype (fp32 in every shipped run).
+    For 16-bit z the scalar stays fp32: rounding it to bf16 would by itself
+    cost 2e-3 relative, the whole bf16 error budget."""
+    return loss.to(z_dtype) if z_dtype in (torch.float32, torch.float64) else loss
+
+
+class SupConFunction(torch.autograd.Function):
+    """loss = SupCon(z, labels): forward keeps O(N) row statistics, backward
+    recomputes the similarity tiles (replaces autograd through reference
+    loss.py:96-153)."""
+
+    @staticmethod
+    def forward(ctx, z, labels_i32, tau, sim_id, lambda_uni, uni_t, topk, alpha, flags):
+        _require_cuda(z, "z")
+        zc = canonical_z(z.detach())
+        n, d = zc.shape
+        prob = make_problem(n, d, _dtype_id(zc), tau=tau, similarity=sim_id, lambda_uni=lambda_uni,
+                            uni_t=uni_t, topk=topk, alpha=alpha, flags=flags)
+        stats, partials, loss = forward_rows(zc, labels_i32, prob, want_loss=True)
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(zc, labels_i32, stats, partials)
+            ctx.prob = prob
+            ctx.in_dtype = z.dtype
+        return _loss_dtype(loss, z.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        zc, labels_i32, stats, partials = ctx.saved_tensors
+        out_dtype = zc.dtype
+        dz = backward_rows(zc, labels_i32, stats, partials, grad_out, ctx.prob, out_dtype=out_dtype)
+        return dz.to(ctx.in_dtype), None, None, None, None, None, None, None, None
+
+
+def supcon_loss(z, labels, *, temperature, similarity="cosine", uniformity_weight=0.0, uniformity_t=2.0,
+                topk_neg=32, alpha=0.0, flags=0) -> torch.Tensor:
+    """Functional form of SupConBinaryLoss.forward (reference loss.py:110-153)."""
+    sim_id = similarity_id(similarity) if isinstance(similarity, str) else int(similarity)
+    n = z.size(0)
+    if n < 2:
+        # reference loss.py:138-139,149: no anchor has a positive and the uniformity term needs B > 1
+        return torch.tensor(0.0, device=z.device, requires_grad=True)
+    lab = canonical_labels(labels, n)
+    return SupConFunction.apply(z, lab, float(temperature), sim_id, float(uniformity_weight),
+                                float(uniformity_t), int(topk_neg), float(alpha), int(flags))
+
+
+class _NormalizeFunction(torch.autograd.Function):
+    """F.normalize(x, p=2, dim=1) (reference stage1_utils.py:123) on the library's kernels."""
+
+    @staticmethod
+    def forward(ctx, x, out_dtype):
+        _require_cuda(x, "x")
+        lib = _cabi.load()
+        xc = x.detach().float().contiguous()
+        n, d = xc.shape
+        dev = xc.device
+        with torch.cuda.device(dev):
+            z = torch.empty((n, d), dtype=out_dtype, device=dev)
+            norms = torch.empty(n, dtype=torch.float32, device=dev)
+            _cabi.check(lib.supcon_normalize_forward(_p(xc), n, d, _p(z), _dtype_id(z), _p(norms), _stream(dev)),
+                        "supcon_normalize_forward")
+        ctx.save_for_backward(z, norms)
+        ctx.in_dtype = x.dtype
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = _cabi.load()
+        z, norms = ctx.saved_tensors
+        if dz.dtype not in (torch.float32, torch.bfloat16):
+            dz = dz.float()
+        dz = dz.contiguous()
+        n, d = z.shape
+        dev = z.device
+        with torch.cuda.device(dev):
+            dx = torch.empty((n, d), dtype=torch.float32, device=dev)
+            _cabi.check(lib.supcon_normalize_backward(_p(z), _dtype_id(z), _p(norms), _p(dz), _dtype_id(dz),
+                                                      n, d, _p(dx), _stream(dev)),
+                        "supcon_normalize_backward")
+        return dx.to(ctx.in_dtype), None
+
+
+def l2_normalize(x: torch.Tensor, out_dtype=torch.float32) -> torch.Tensor:
+    return _NormalizeFunction.apply(x, out_dtype)
