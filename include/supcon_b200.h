@@ -137,6 +137,12 @@ int supcon_normalize_backward(const void* z, int32_t z_dtype, const float* norms
 int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
                         const float* row_stats, int32_t* idx_out /*[n_rows][topk]*/, void* stream);
 
+/* Diagnostic for the tcgen05/TMA building blocks (tests only): for 128-row blocks
+ * I = row_i.., J = row_j.. of a bf16 matrix z [n][256] writes S = Z_I Z_J^T
+ * ([128][128] fp32) and O = bf16(S) Z_J ([128][256] fp32). */
+int supcon_debug_tc_tile(const void* z_bf16, int32_t n, int32_t d, int32_t row_i, int32_t row_j,
+                         float* s_out, float* o_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ ST_LSE, ST_LSE_M, ST_NPOS, ST_NNEG, ST_THR_VAL, ST_THR_IDX, ST_WSUM, ST_POS_MEAN
 EXPORTS = (
     "supcon_abi_version", "supcon_last_error", "supcon_workspace_bytes", "supcon_forward_rows",
     "supcon_finalize", "supcon_backward_rows", "supcon_loss_and_grad", "supcon_normalize_forward",
-    "supcon_normalize_backward", "supcon_topk_indices",
+    "supcon_normalize_backward", "supcon_topk_indices", "supcon_debug_tc_tile",
 )
 
 
@@ -76,6 +76,8 @@ def load():
                                               c_int32, c_void_p, c_void_p]
     lib.supcon_topk_indices.restype = c_int32
     lib.supcon_topk_indices.argtypes = [P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.supcon_debug_tc_tile.restype = c_int32
+    lib.supcon_debug_tc_tile.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     if lib.supcon_abi_version() != 1:
         raise RuntimeError("libsupcon_b200.so ABI version mismatch")
     _lib = lib

@@ -244,4 +244,13 @@ int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int3
   return 0;
 }
 
+int supcon_debug_tc_tile(const void* z_bf16, int32_t n, int32_t d, int32_t row_i, int32_t row_j, float* s_out,
+                         float* o_out, void* stream) {
+  if (!z_bf16 || !s_out || !o_out) return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_debug_tc_tile");
+  const char* err = "";
+  int rc = tc_debug_tile(z_bf16, n, d, row_i, row_j, s_out, o_out, reinterpret_cast<cudaStream_t>(stream), &err);
+  if (rc) return fail(rc, "supcon_debug_tc_tile: %s", err);
+  return 0;
+}
+
 }  // extern "C"

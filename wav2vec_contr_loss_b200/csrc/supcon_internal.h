@@ -30,4 +30,8 @@ cudaError_t ffma_forward(const FfmaArgs& a, cudaStream_t stream);
 cudaError_t ffma_backward(const FfmaArgs& a, int dz_dtype, cudaStream_t stream);
 cudaError_t ffma_topk_indices(const FfmaArgs& a, int32_t* idx_out, cudaStream_t stream);
 
+// tcgen05 building-block diagnostic (supcon_tc_debug.cu)
+int tc_debug_tile(const void* z_bf16, int n, int d, int row_i, int row_j, float* s_out, float* o_out,
+                  cudaStream_t stream, const char** err);
+
 }  // namespace supcon
