@@ -48,6 +48,26 @@ int validate(const supcon_problem_t* p) {
   return 0;
 }
 
+// internal debug flags (tests): take the tensor path for only one direction
+constexpr uint32_t FLAG_TC_FWD_ONLY = 8u, FLAG_TC_BWD_ONLY = 16u;
+
+bool use_tc(const supcon_problem_t* p, bool backward) {
+  if (p->flags & SUPCON_FLAG_FORCE_EXACT) return false;
+  if (!tc_supported(p)) return false;
+  if (backward && (p->flags & FLAG_TC_FWD_ONLY)) return false;
+  if (!backward && (p->flags & FLAG_TC_BWD_ONLY)) return false;
+  return true;
+}
+
+size_t workspace_need(const supcon_problem_t* p) {
+  size_t need = ffma_workspace_bytes(p->n_rows);
+  if (!(p->flags & SUPCON_FLAG_FORCE_EXACT) && tc_supported(p)) {
+    size_t t = tc_plan(p).total_bytes;
+    if (t > need) need = t;
+  }
+  return need;
+}
+
 bool needs_mining(const supcon_problem_t* p) { return p->alpha != 0.f && p->topk >= 1; }
 
 bool vec_ok(const void* z, const supcon_problem_t* p) {
@@ -126,7 +146,7 @@ const char* supcon_last_error(void) { return g_err.c_str(); }
 int supcon_workspace_bytes(const supcon_problem_t* p, size_t* bytes_out) {
   if (int rc = validate(p)) return rc;
   if (!bytes_out) return fail(SUPCON_E_INVALID, "bytes_out is NULL");
-  *bytes_out = ffma_workspace_bytes(p->n_rows);
+  *bytes_out = workspace_need(p);
   return 0;
 }
 
@@ -136,12 +156,19 @@ int supcon_forward_rows(const supcon_problem_t* p, const void* z_all, const int3
   if (int rc = validate(p)) return rc;
   if (!z_all || !labels_all || !row_stats || !partials || !workspace)
     return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_forward_rows");
-  if (workspace_bytes < ffma_workspace_bytes(p->n_rows))
-    return fail(SUPCON_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes,
-                ffma_workspace_bytes(p->n_rows));
+  if (workspace_bytes < workspace_need(p))
+    return fail(SUPCON_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, workspace_need(p));
+  if ((p->flags & SUPCON_FLAG_FORCE_TENSOR) && !tc_supported(p))
+    return fail(SUPCON_E_UNSUPPORTED, "tensor-core path needs bf16 z, d == 256, tau >= 0.025, N >= 256, no mining");
   if (loss_out && (p->row_offset != 0 || p->n_rows != p->n_total))
     return fail(SUPCON_E_INVALID, "loss_out needs a rank that owns every row; use supcon_finalize");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use_tc(p, false)) {
+    const char* err = "";
+    int rc = tc_forward(p, z_all, labels_all, row_stats, partials, loss_out, workspace, st, &err);
+    if (rc) return fail(rc, "tc_forward: %s", err);
+    return 0;
+  }
   cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   FfmaArgs a = make_ffma(p, z_all, labels_all, workspace);
@@ -171,7 +198,15 @@ int supcon_backward_rows(const supcon_problem_t* p, const void* z_all, const int
     return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_backward_rows");
   if (dz_dtype != SUPCON_F32 && dz_dtype != SUPCON_BF16)
     return fail(SUPCON_E_INVALID, "unknown dz_dtype %d", dz_dtype);
-  (void)workspace_bytes;
+  if (use_tc(p, true)) {
+    if (!workspace || workspace_bytes < workspace_need(p))
+      return fail(SUPCON_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, workspace_need(p));
+    const char* err = "";
+    int rc = tc_backward(p, z_all, labels_all, stats_all, partials_global, grad_out, dz_out, dz_dtype, workspace,
+                         reinterpret_cast<cudaStream_t>(stream), &err);
+    if (rc) return fail(rc, "tc_backward: %s", err);
+    return 0;
+  }
   FfmaArgs a = make_ffma(p, z_all, labels_all, workspace ? workspace : (void*)dz_out);
   a.stats_all = stats_all;
   a.partials = const_cast<double*>(partials_global);

@@ -80,6 +80,54 @@ __device__ __forceinline__ GlobalCoef global_coef(const double* pg, int n_total,
   return g;
 }
 
+// Fixed-order block reduction of the per-row loss terms -> workspace; the last
+// block to finish sums over blocks (fixed order, deterministic) into partials[]
+// and optionally writes the scalar loss.  red = [5][rows] doubles in shared memory.
+struct FinishArgs {
+  double* block_partials;  // [gridDim.x][SUPCON_N_PARTIALS]
+  unsigned* ticket;        // zero before the launch
+  double* partials;        // [SUPCON_N_PARTIALS] out
+  float* loss_out;         // optional
+  int n_total;
+  float tau, alpha, lambda_uni, uni_t;
+};
+
+__device__ inline void block_partials_and_finish(const FinishArgs& a, const double* red, int rows) {
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  double* bp = a.block_partials + (int64_t)blockIdx.x * SUPCON_N_PARTIALS;
+  if (tid < 5) {
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += red[tid * rows + r];
+    bp[tid] = s;
+  } else if (tid < SUPCON_N_PARTIALS) {
+    bp[tid] = 0.0;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned t = atomicAdd(a.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid < SUPCON_N_PARTIALS) {
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b)
+      s += *((volatile double*)(a.block_partials + (int64_t)b * SUPCON_N_PARTIALS + tid));
+    a.partials[tid] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *a.ticket = 0u;
+    if (a.loss_out) {
+      GlobalCoef g = global_coef(a.partials, a.n_total, a.tau, a.alpha, a.lambda_uni, a.uni_t);
+      *a.loss_out = g.loss;
+    }
+  }
+}
+
 // ---- element access for fp32 / bf16 row-major matrices ----
 template <typename T>
 __device__ __forceinline__ float ld_elem(const T* p);

@@ -84,44 +84,6 @@ __device__ __forceinline__ void gram_tile(const T* __restrict__ z, int d, bool v
   }
 }
 
-// Fixed-order block reduction -> workspace; last block sums over blocks (fixed
-// order) into partials[] and optionally writes the loss.
-__device__ void block_partials_and_finish(const FfmaArgs& a, const double* red, int rows) {
-  __shared__ int is_last;
-  const int tid = threadIdx.x;
-  double* bp = a.block_partials + (int64_t)blockIdx.x * SUPCON_N_PARTIALS;
-  if (tid < 5) {
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += red[tid * rows + r];
-    bp[tid] = s;
-  } else if (tid < SUPCON_N_PARTIALS) {
-    bp[tid] = 0.0;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    unsigned t = atomicAdd(a.ticket, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  if (tid < SUPCON_N_PARTIALS) {
-    double s = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b)
-      s += *((volatile double*)(a.block_partials + (int64_t)b * SUPCON_N_PARTIALS + tid));
-    a.partials[tid] = s;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    *a.ticket = 0u;  // self-reset for the next launch
-    if (a.loss_out) {
-      GlobalCoef g = global_coef(a.partials, a.n_total, a.tau, a.alpha, a.lambda_uni, a.uni_t);
-      *a.loss_out = g.loss;
-    }
-  }
-}
-
 // row-state of the online softmax held by each of the 4 threads of a row
 struct RowAcc {
   float m, sum_all, sum_pos_e, sum_pos_s, wsum;
@@ -336,7 +298,8 @@ __global__ void __launch_bounds__(NT) ffma_fwd_kernel(FfmaArgs a) {
     red[3 * BM + pr] = c_mined; red[4 * BM + pr] = w;
   }
   __syncthreads();
-  block_partials_and_finish(a, red, BM);
+  FinishArgs fa{a.block_partials, a.ticket, a.partials, a.loss_out, a.n_total, a.tau, a.alpha, a.lambda_uni, a.uni_t};
+  block_partials_and_finish(fa, red, BM);
 }
 
 // ---------------------------------------------------------------------------

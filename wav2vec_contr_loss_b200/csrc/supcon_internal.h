@@ -30,6 +30,46 @@ cudaError_t ffma_forward(const FfmaArgs& a, cudaStream_t stream);
 cudaError_t ffma_backward(const FfmaArgs& a, int dz_dtype, cudaStream_t stream);
 cudaError_t ffma_topk_indices(const FfmaArgs& a, int32_t* idx_out, cudaStream_t stream);
 
+// ---- bf16 tensor-core path (supcon_tc.cu) ----
+struct TcPlan {
+  int n_pad, rows_pad, row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_splits, bwd_splits, merge_blocks;
+  size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
+      off_scalars, off_part, total_bytes;
+};
+struct TcFwdArgs {
+  const int32_t* lab_pad;
+  const float* nrm_pad;
+  float* part;  // [splits][rows_pad][4]
+  int n_total, n_pad, row_offset, n_rows, rows_pad, splits, col_tiles, topk;
+  float inv_tau, c1, c0, ut2;
+};
+struct TcBwdPrepArgs {
+  const float* stats_all;
+  const double* partials;
+  const int32_t* labels;
+  float *colA, *colAm, *colB, *colThr;
+  int32_t *colThrIdx, *lab_pad;
+  float* scalars;
+  int n_total, n_pad, topk;
+  float tau, alpha, lambda_uni, uni_t;
+};
+struct TcBwdArgs {
+  const int32_t* lab_pad;
+  const float* nrm_pad;
+  const float *colA, *colB;
+  const float* scalars;  // [0] = uniformity coefficient cu
+  float* dz_part;        // [splits][rows_pad][256]
+  int n_total, n_pad, row_offset, n_rows, rows_pad, splits, col_tiles;
+  float c1, c0, ut2;
+};
+TcPlan tc_plan(const supcon_problem_t* p);
+bool tc_supported(const supcon_problem_t* p);
+int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, float* row_stats,
+               double* partials, float* loss_out, void* workspace, cudaStream_t stream, const char** err);
+int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, const float* stats_all,
+                const double* partials_global, const float* grad_out, void* dz_out, int dz_dtype, void* workspace,
+                cudaStream_t stream, const char** err);
+
 // tcgen05 building-block diagnostic (supcon_tc_debug.cu)
 int tc_debug_tile(const void* z_bf16, int n, int d, int row_i, int row_j, float* s_out, float* o_out,
                   cudaStream_t stream, const char** err);

@@ -1,0 +1,743 @@
+// bf16 tensor-core SupCon path (sm_100a): tcgen05.mma with TMA-staged tiles and
+// TMEM accumulators, fused flash-style with the similarity transform, masks,
+// exp / log-sum-exp and (backward) the formation of H = G + G^T, so the N x N
+// matrix never reaches HBM.
+//
+//   forward  : per CTA a 128-row block I and a range of 128-column tiles J.
+//              S_IJ = Z_I Z_J^T (16 x tcgen05.mma 128x128x16) into one of two
+//              TMEM buffers; two softmax warpgroups drain alternate buffers.
+//              Every similarity is <= 1, so exp uses the fixed maximum 1/tau
+//              (no online rescale).  Output: per-row partial sums
+//              per column split; a merge kernel turns them into row statistics.
+//   backward : per CTA a 128-row block I and a range of 64-column tiles J.
+//              S_IJ recomputed (tcgen05 128x64x16), H_IJ formed in registers
+//              from row/column coefficient vectors, written as bf16 into
+//              128B-swizzled smem, then dZ_I += H_IJ Z_J (tcgen05 128x256x16,
+//              Z_J tile reused MN-major) accumulating in TMEM.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM
+// alloc), warps 2..9 = eight softmax/epilogue warps (two warpgroups).
+// Preconditions of this path (checked by the dispatcher): bf16 z, d == 256,
+// tau >= 0.025, rows L2-normalised (what the callers pass, stage1_utils.py:123).
+#include "supcon_common.cuh"
+#include "supcon_internal.h"
+#include "tc_ptx.cuh"
+#include "tc_tmap.cuh"
+
+namespace supcon {
+namespace {
+
+constexpr int TBM = 128;                  // rows per CTA
+constexpr int TD = 256;                   // embedding width handled here
+constexpr int NBOX = TD / 64;             // 64-column (128-byte) TMA boxes per row
+constexpr int NTHREADS = 320;
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// acos on [-1,1]: sqrt(1-|x|) * P7(|x|) (Abramowitz-Stegun 4.4.46, |err| <= 2e-8)
+__device__ __forceinline__ float acos_fast(float x) {
+  float ax = fabsf(x);
+  float p = -0.0012624911f;
+  p = fmaf(p, ax, 0.0066700901f);
+  p = fmaf(p, ax, -0.0170881256f);
+  p = fmaf(p, ax, 0.0308918810f);
+  p = fmaf(p, ax, -0.0501743046f);
+  p = fmaf(p, ax, 0.0889789874f);
+  p = fmaf(p, ax, -0.2145988016f);
+  p = fmaf(p, ax, 1.5707963050f);
+  float r = sqrt_approx(1.0f - ax) * p;
+  return x < 0.f ? SUPCON_PI_F - r : r;
+}
+__device__ __forceinline__ float geodesic_sim_fast(float c) {
+  float ch = fminf(fmaxf(c, -geo_hi()), geo_hi());
+  return fmaf(-SUPCON_2_OVER_PI_F, acos_fast(ch), 1.0f);
+}
+__device__ __forceinline__ float geodesic_slope_fast(float c) {
+  float inside = (c >= -geo_hi() && c <= geo_hi()) ? SUPCON_2_OVER_PI_F : 0.f;
+  float ch = fminf(fmaxf(c, -geo_hi()), geo_hi());
+  return inside * rsqrt_approx(fmaf(-ch, ch, 1.0f));
+}
+
+// ---------------------------------------------------------------------------
+// prep: padded labels / squared norms (forward) and column coefficients (backward)
+// ---------------------------------------------------------------------------
+__global__ void tc_prep_fwd_kernel(const __nv_bfloat16* __restrict__ z, const int32_t* __restrict__ labels, int n,
+                                   int n_pad, int d, int32_t* __restrict__ lab_pad, float* __restrict__ nrm_pad,
+                                   int want_norms) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_pad) return;
+  float s = 0.f;
+  if (warp < n && want_norms) {
+    const __nv_bfloat16* zr = z + (int64_t)warp * d;
+    for (int k = lane; k < d; k += 32) { float v = __bfloat162float(zr[k]); s = fmaf(v, v, s); }
+    s = warp_sum(s);
+  }
+  if (lane == 0) {
+    lab_pad[warp] = warp < n ? labels[warp] : 0;
+    if (want_norms) nrm_pad[warp] = warp < n ? s : 0.f;
+  }
+}
+
+// column coefficient vectors of H (SURVEY Appendix A with the fixed maximum 1/tau):
+//   e0_ij = exp((s_ij - 1)/tau);  H_ij = e0 (A_i + A_j) [+ mined terms] - pos_ij (B_i + B_j)
+//   A = a_f exp(1/tau - lse),  Am = a_m exp(1/tau - lse_m),  B = (a_f + a_m)/|pos|
+__global__ void tc_prep_bwd_kernel(TcBwdPrepArgs a) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n_pad) return;
+  float A = 0.f, Am = 0.f, B = 0.f, thr = INFINITY;
+  int ti = -1, lab = 0;
+  if (j < a.n_total) {
+    const GlobalCoef g = global_coef(a.partials, a.n_total, a.tau, a.alpha, a.lambda_uni, a.uni_t);
+    const float* s = a.stats_all + (int64_t)j * SUPCON_STATS_STRIDE;
+    const int* si = reinterpret_cast<const int*>(s);
+    int npos = si[SUPCON_ST_NPOS], nneg = si[SUPCON_ST_NNEG];
+    bool in_f = npos > 0, in_m = in_f && nneg > 0 && a.topk >= 1;
+    float af = in_f ? g.a_full : 0.f, am = in_m ? g.a_mined : 0.f;
+    float inv_tau = 1.0f / a.tau;
+    A = af * expf(inv_tau - s[SUPCON_ST_LSE]);
+    Am = (am != 0.f) ? am * expf(inv_tau - s[SUPCON_ST_LSE_M]) : 0.f;
+    B = in_f ? (af + am) / (float)npos : 0.f;
+    thr = s[SUPCON_ST_THR_VAL];
+    ti = si[SUPCON_ST_THR_IDX];
+    lab = a.labels[j];
+    if (j == 0) a.scalars[0] = g.cu;
+  }
+  a.colA[j] = A; a.colAm[j] = Am; a.colB[j] = B; a.colThr[j] = thr; a.colThrIdx[j] = ti; a.lab_pad[j] = lab;
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+struct RowSums {
+  float sum_all, sum_pos_s, wsum;
+  int npos;
+};
+
+template <int SIM, bool UNI, bool MASKED>
+__device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int gi, int n_total, int lab_r,
+                                          float nrm_r, const int32_t* __restrict__ lab_pad,
+                                          const float* __restrict__ nrm_pad, float c1, float c0, float ut2,
+                                          RowSums& st) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int4 lb = __ldg(reinterpret_cast<const int4*>(lab_pad + gj0 + 4 * q));
+    float4 nj = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (UNI) nj = __ldg(reinterpret_cast<const float4*>(nrm_pad + gj0 + 4 * q));
+    const int labs[4] = {lb.x, lb.y, lb.z, lb.w};
+    const float njs[4] = {nj.x, nj.y, nj.z, nj.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float c = __uint_as_float(r[4 * q + e]);
+      const float s = (SIM == SUPCON_GEODESIC) ? geodesic_sim_fast(c) : c;
+      float ex = ex2f(fmaf(s, c1, c0));
+      bool pos = labs[e] == lab_r;
+      if (MASKED) {
+        const int gj = gj0 + 4 * q + e;
+        const bool valid = gj < n_total && gj != gi;
+        ex = valid ? ex : 0.f;
+        pos = pos && valid;
+      }
+      st.sum_all += ex;
+      if (pos) { st.sum_pos_s += s; st.npos++; }
+      if (UNI) {
+        float w = ex2f(-ut2 * fmaxf(nrm_r + njs[e] - 2.f * c, 0.f));
+        if (MASKED) {
+          const int gj = gj0 + 4 * q + e;
+          w = (gj < n_total && gj != gi) ? w : 0.f;
+        }
+        st.wsum += w;
+      }
+    }
+  }
+}
+
+template <int SIM, bool UNI>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
+  constexpr int BN = 128;
+  constexpr uint32_t BOX_BYTES = 128 * 128;         // 128 rows x 128 B
+  constexpr uint32_t TILE_BYTES = NBOX * BOX_BYTES;  // 64 KB
+  constexpr int STAGES = 2;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sZI = smem;
+  unsigned char* sZJ = smem + TILE_BYTES;
+  __shared__ __align__(8) uint64_t bar_zi, bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float comb[TBM][4];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rb = blockIdx.x / a.splits, split = blockIdx.x % a.splits;
+  const int row0 = a.row_offset + rb * TBM;
+  const int ct_begin = (int)(((int64_t)a.col_tiles * split) / a.splits);
+  const int ct_end = (int)(((int64_t)a.col_tiles * (split + 1)) / a.splits);
+  const int ntiles = ct_end - ct_begin;
+
+  if (tid == 0) {
+    ptx::mbar_init(&bar_zi, 1);
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_tfull[b], 1); ptx::mbar_init(&bar_tempty[b], 128); }
+    ptx::fence_mbar_init();
+    ptx::tma_prefetch_desc(&tmap);
+  }
+  if (warp == 1) ptx::tmem_alloc<256>(&tmem_base_s);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      ptx::mbar_expect_tx(&bar_zi, TILE_BYTES);
+      for (int b = 0; b < NBOX; ++b) ptx::tma_load_2d(sZI + b * BOX_BYTES, &tmap, &bar_zi, 64 * b, row0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int st = t % STAGES, use = t / STAGES;
+        ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
+        ptx::mbar_expect_tx(&bar_full[st], TILE_BYTES);
+        for (int b = 0; b < NBOX; ++b)
+          ptx::tma_load_2d(sZJ + st * TILE_BYTES + b * BOX_BYTES, &tmap, &bar_full[st], 64 * b, (ct_begin + t) * BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16(128, BN, false, false);
+      const uint32_t a0 = ptx::smem_u32(sZI);
+      ptx::mbar_wait(&bar_zi, 0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int st = t % STAGES, use = t / STAGES, buf = t & 1, buse = t >> 1;
+        ptx::mbar_wait(&bar_full[st], use & 1);
+        ptx::mbar_wait(&bar_tempty[buf], (buse & 1) ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t b0 = ptx::smem_u32(sZJ + st * TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < TD / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * BOX_BYTES + (ks & 3) * 32;
+          ptx::mma_ss(tmem + buf * BN, ptx::smem_desc_sw128(a0 + off, 16, 1024),
+                      ptx::smem_desc_sw128(b0 + off, 16, 1024), idesc, ks > 0);
+        }
+        ptx::mma_commit(&bar_empty[st]);
+        ptx::mma_commit(&bar_tfull[buf]);
+      }
+    }
+  } else {
+    // ===== softmax warpgroups: warps 2-5 drain buffer 0 (even tiles), warps 6-9 buffer 1 =====
+    const int wg = (warp - 2) >> 2;
+    const int lrow = 32 * (warp & 3) + lane;  // TMEM lane == row of the block
+    const int gi = row0 + lrow;
+    const int lab_r = a.lab_pad[min(gi, a.n_pad - 1)];
+    const float nrm_r = UNI ? a.nrm_pad[min(gi, a.n_pad - 1)] : 0.f;
+    RowSums st;
+    st.sum_all = 0.f; st.sum_pos_s = 0.f; st.wsum = 0.f; st.npos = 0;
+    for (int t = wg; t < ntiles; t += 2) {
+      const int buf = wg, buse = t >> 1;
+      const int col0 = (ct_begin + t) * BN;
+      ptx::mbar_wait(&bar_tfull[buf], buse & 1);
+      ptx::tc_fence_after_sync();
+      const bool masked = (col0 + BN > a.n_total) || (col0 < row0 + TBM && row0 < col0 + BN);
+      const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + 32 * c, r);
+        ptx::tmem_ld_wait();
+        if (masked)
+          fwd_chunk<SIM, UNI, true>(r, col0 + 32 * c, gi, a.n_total, lab_r, nrm_r, a.lab_pad, a.nrm_pad, a.c1, a.c0,
+                                    a.ut2, st);
+        else
+          fwd_chunk<SIM, UNI, false>(r, col0 + 32 * c, gi, a.n_total, lab_r, nrm_r, a.lab_pad, a.nrm_pad, a.c1, a.c0,
+                                     a.ut2, st);
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&bar_tempty[buf]);
+    }
+    if (wg == 1) {
+      comb[lrow][0] = st.sum_all; comb[lrow][1] = st.sum_pos_s; comb[lrow][2] = st.wsum;
+      comb[lrow][3] = __int_as_float(st.npos);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (wg == 0 && gi < a.row_offset + a.n_rows) {
+      float* out = a.part + ((int64_t)split * a.rows_pad + (gi - a.row_offset)) * 4;
+      float4 v;
+      v.x = st.sum_all + comb[lrow][0];
+      v.y = st.sum_pos_s + comb[lrow][1];
+      v.z = st.wsum + comb[lrow][2];
+      v.w = __int_as_float(st.npos + __float_as_int(comb[lrow][3]));
+      *reinterpret_cast<float4*>(out) = v;
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<256>(tmem);
+}
+
+// merge the column splits into row statistics + loss partial sums
+__global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishArgs f, float* __restrict__ row_stats) {
+  __shared__ double red[5 * 128];
+  const int lr = blockIdx.x * 128 + threadIdx.x;
+  double l_full = 0.0, c_full = 0.0, l_mined = 0.0, c_mined = 0.0, w = 0.0;
+  if (lr < a.n_rows) {
+    float sum_all = 0.f, sum_pos_s = 0.f, wsum = 0.f;
+    int npos = 0;
+    for (int s = 0; s < a.splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(a.part + ((int64_t)s * a.rows_pad + lr) * 4);
+      sum_all += v.x; sum_pos_s += v.y; wsum += v.z; npos += __float_as_int(v.w);
+    }
+    const int nneg = a.n_total - 1 - npos;
+    const float lse = logf(sum_all) + a.inv_tau;   // fixed maximum 1/tau folded back in
+    const float pos_mean = npos > 0 ? (sum_pos_s * a.inv_tau) / (float)npos : 0.f;
+    float* so = row_stats + (int64_t)lr * SUPCON_STATS_STRIDE;
+    so[SUPCON_ST_LSE] = lse;
+    so[SUPCON_ST_LSE_M] = lse;
+    reinterpret_cast<int*>(so)[SUPCON_ST_NPOS] = npos;
+    reinterpret_cast<int*>(so)[SUPCON_ST_NNEG] = nneg;
+    so[SUPCON_ST_THR_VAL] = a.topk >= 1 ? -INFINITY : INFINITY;
+    reinterpret_cast<int*>(so)[SUPCON_ST_THR_IDX] = a.topk >= 1 ? SUPCON_INT_MAX : -1;
+    so[SUPCON_ST_WSUM] = wsum;
+    so[SUPCON_ST_POS_MEAN] = pos_mean;
+    if (npos > 0) {
+      l_full = (double)(lse - pos_mean); c_full = 1.0;
+      if (nneg > 0 && a.topk >= 1) { l_mined = l_full; c_mined = 1.0; }
+    }
+    w = (double)wsum;
+  }
+  red[0 * 128 + threadIdx.x] = l_full; red[1 * 128 + threadIdx.x] = c_full; red[2 * 128 + threadIdx.x] = l_mined;
+  red[3 * 128 + threadIdx.x] = c_mined; red[4 * 128 + threadIdx.x] = w;
+  __syncthreads();
+  block_partials_and_finish(f, red, 128);
+}
+
+// ---------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------
+template <int SIM, bool UNI, bool MASKED>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw)[16], int gj0, int gi, int lab_r,
+                                          float A_r, float B_r, float nrm_r, float cu, const TcBwdArgs& a) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int4 lb = __ldg(reinterpret_cast<const int4*>(a.lab_pad + gj0 + 4 * q));
+    const float4 Aj = __ldg(reinterpret_cast<const float4*>(a.colA + gj0 + 4 * q));
+    const float4 Bj = __ldg(reinterpret_cast<const float4*>(a.colB + gj0 + 4 * q));
+    float4 nj = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (UNI) nj = __ldg(reinterpret_cast<const float4*>(a.nrm_pad + gj0 + 4 * q));
+    const int labs[4] = {lb.x, lb.y, lb.z, lb.w};
+    const float As[4] = {Aj.x, Aj.y, Aj.z, Aj.w};
+    const float Bs[4] = {Bj.x, Bj.y, Bj.z, Bj.w};
+    const float njs[4] = {nj.x, nj.y, nj.z, nj.w};
+    float h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float c = __uint_as_float(r[4 * q + e]);
+      const float s = (SIM == SUPCON_GEODESIC) ? geodesic_sim_fast(c) : c;
+      const float e0 = ex2f(fmaf(s, a.c1, a.c0));
+      float v = e0 * (A_r + As[e]);
+      if (labs[e] == lab_r) v -= B_r + Bs[e];
+      if (SIM == SUPCON_GEODESIC) v *= geodesic_slope_fast(c);
+      if (UNI) v = fmaf(-cu, ex2f(-a.ut2 * fmaxf(nrm_r + njs[e] - 2.f * c, 0.f)), v);
+      if (MASKED) v = (gj0 + 4 * q + e == gi) ? 0.f : v;
+      h[e] = v;
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(h[0], h[1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(h[2], h[3]);
+    hw[2 * q] = *reinterpret_cast<uint32_t*>(&p0);
+    hw[2 * q + 1] = *reinterpret_cast<uint32_t*>(&p1);
+  }
+}
+
+template <int SIM, bool UNI>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapI,
+                                                             const __grid_constant__ CUtensorMap tmapJ, TcBwdArgs a) {
+  constexpr int BN = 64;
+  constexpr int STAGES = 3;
+  constexpr uint32_t BOXI_BYTES = 128 * 128;            // Z_I boxes: 128 rows
+  constexpr uint32_t TILEI_BYTES = NBOX * BOXI_BYTES;   // 64 KB
+  constexpr uint32_t BOXJ_BYTES = BN * 128;             // Z_J boxes: 64 rows
+  constexpr uint32_t TILEJ_BYTES = NBOX * BOXJ_BYTES;   // 32 KB
+  constexpr uint32_t H_BYTES = TBM * BN * 2;            // 16 KB
+  constexpr uint32_t TM_DZ = 0, TM_S = 256;             // TMEM columns: dZ [0,256), S buffers 256 + 64 b
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sZI = smem;
+  unsigned char* sZJ = sZI + TILEI_BYTES;
+  unsigned char* sH = sZJ + STAGES * TILEJ_BYTES;
+  __shared__ __align__(8) uint64_t bar_zi, bar_full[STAGES], bar_empty[STAGES], bar_sfull[2], bar_sempty[2],
+      bar_hfull[2], bar_hempty[2], bar_done;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rb = blockIdx.x / a.splits, split = blockIdx.x % a.splits;
+  const int row0 = a.row_offset + rb * TBM;
+  const int ct_begin = (int)(((int64_t)a.col_tiles * split) / a.splits);
+  const int ct_end = (int)(((int64_t)a.col_tiles * (split + 1)) / a.splits);
+  const int ntiles = ct_end - ct_begin;
+
+  if (tid == 0) {
+    ptx::mbar_init(&bar_zi, 1);
+    ptx::mbar_init(&bar_done, 1);
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_sempty[b], 256);
+      ptx::mbar_init(&bar_hfull[b], 256); ptx::mbar_init(&bar_hempty[b], 1);
+    }
+    ptx::fence_mbar_init();
+    ptx::tma_prefetch_desc(&tmapI);
+    ptx::tma_prefetch_desc(&tmapJ);
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(&tmem_base_s);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      ptx::mbar_expect_tx(&bar_zi, TILEI_BYTES);
+      for (int b = 0; b < NBOX; ++b) ptx::tma_load_2d(sZI + b * BOXI_BYTES, &tmapI, &bar_zi, 64 * b, row0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int st = t % STAGES, use = t / STAGES;
+        ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
+        ptx::mbar_expect_tx(&bar_full[st], TILEJ_BYTES);
+        for (int b = 0; b < NBOX; ++b)
+          ptx::tma_load_2d(sZJ + st * TILEJ_BYTES + b * BOXJ_BYTES, &tmapJ, &bar_full[st], 64 * b,
+                           (ct_begin + t) * BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: iteration t issues S(t) and then dZ(t-1) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::idesc_bf16(128, BN, false, false);
+      constexpr uint32_t idesc_dz = ptx::idesc_bf16(128, TD, false, true);
+      const uint32_t a0 = ptx::smem_u32(sZI);
+      ptx::mbar_wait(&bar_zi, 0);
+      for (int t = 0; t <= ntiles; ++t) {
+        if (t < ntiles) {
+          const int st = t % STAGES, use = t / STAGES, buf = t & 1, buse = t >> 1;
+          ptx::mbar_wait(&bar_full[st], use & 1);
+          ptx::mbar_wait(&bar_sempty[buf], (buse & 1) ^ 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < TD / 16; ++ks) {
+            const uint32_t offa = (ks >> 2) * BOXI_BYTES + (ks & 3) * 32;
+            const uint32_t offb = (ks >> 2) * BOXJ_BYTES + (ks & 3) * 32;
+            ptx::mma_ss(tmem + TM_S + buf * BN, ptx::smem_desc_sw128(a0 + offa, 16, 1024),
+                        ptx::smem_desc_sw128(b0 + offb, 16, 1024), idesc_s, ks > 0);
+          }
+          ptx::mma_commit(&bar_sfull[buf]);
+        }
+        if (t >= 1) {
+          const int tt = t - 1;
+          const int st = tt % STAGES, buf = tt & 1, buse = tt >> 1;
+          ptx::mbar_wait(&bar_hfull[buf], buse & 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t h0 = ptx::smem_u32(sH + buf * H_BYTES);
+          const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            ptx::mma_ss(tmem + TM_DZ, ptx::smem_desc_sw128(h0 + kk * 32, 16, 1024),
+                        ptx::smem_desc_sw128(b0 + kk * 16 * 128, BOXJ_BYTES, 1024), idesc_dz, (tt > 0 || kk > 0));
+          }
+          ptx::mma_commit(&bar_empty[st]);
+          ptx::mma_commit(&bar_hempty[buf]);
+        }
+      }
+      ptx::mma_commit(&bar_done);
+    }
+  } else {
+    // ===== H warpgroups: both work on every tile; warpgroup g takes columns 32g..32g+31 =====
+    const int wg = (warp - 2) >> 2;
+    const int lrow = 32 * (warp & 3) + lane;
+    const int gi = row0 + lrow;
+    const int gic = min(gi, a.n_pad - 1);
+    const int lab_r = a.lab_pad[gic];
+    const float A_r = a.colA[gic], B_r = a.colB[gic];
+    const float nrm_r = UNI ? a.nrm_pad[gic] : 0.f;
+    const float cu = UNI ? a.scalars[0] : 0.f;
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1, buse = t >> 1;
+      const int col0 = (ct_begin + t) * BN;
+      ptx::mbar_wait(&bar_sfull[buf], buse & 1);
+      ptx::tc_fence_after_sync();
+      uint32_t r[32];
+      ptx::tmem_ld32(tmem + lane_addr + TM_S + buf * BN + 32 * wg, r);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&bar_sempty[buf]);
+      uint32_t hw[16];
+      const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
+      if (masked) bwd_chunk<SIM, UNI, true>(r, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, a);
+      else bwd_chunk<SIM, UNI, false>(r, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, a);
+      ptx::mbar_wait(&bar_hempty[buf], (buse & 1) ^ 1);
+      const uint32_t hbase = ptx::smem_u32(sH + buf * H_BYTES) + lrow * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = 4 * wg + q;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hbase + ((chunk ^ (lrow & 7)) << 4)),
+                     "r"(hw[4 * q]), "r"(hw[4 * q + 1]), "r"(hw[4 * q + 2]), "r"(hw[4 * q + 3])
+                     : "memory");
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&bar_hfull[buf]);
+    }
+    // ---- epilogue: dZ rows out of TMEM; warpgroup g writes columns 128g..128g+127 ----
+    ptx::mbar_wait(&bar_done, 0);
+    ptx::tc_fence_after_sync();
+    const bool row_ok = gi < a.row_offset + a.n_rows;
+    float* outp = a.dz_part + ((int64_t)split * a.rows_pad + (gi - a.row_offset)) * TD + 128 * wg;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tmem + lane_addr + TM_DZ + 128 * wg + 32 * c, r);
+      ptx::tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(outp + 32 * c + 4 * q) =
+              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                          __uint_as_float(r[4 * q + 3]));
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem);
+}
+
+// sum the column splits, add the uniformity diagonal term, scale by grad_out, convert
+template <typename TO>
+__global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const __nv_bfloat16* __restrict__ z,
+                                                            const float* __restrict__ stats_all,
+                                                            const float* __restrict__ grad_out, TO* __restrict__ out) {
+  const int64_t idx4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of one row
+  const int per_row = TD / 4;
+  const int lr = (int)(idx4 / per_row), c4 = (int)(idx4 % per_row);
+  if (lr >= a.n_rows) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < a.splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(a.dz_part + ((int64_t)s * a.rows_pad + lr) * TD + 4 * c4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const int gi = a.row_offset + lr;
+  const float cu = a.scalars[0];
+  if (cu != 0.f) {
+    const float wd = cu * stats_all[(int64_t)gi * SUPCON_STATS_STRIDE + SUPCON_ST_WSUM];
+    const __nv_bfloat16* zr = z + (int64_t)gi * TD + 4 * c4;
+    acc.x = fmaf(wd, __bfloat162float(zr[0]), acc.x); acc.y = fmaf(wd, __bfloat162float(zr[1]), acc.y);
+    acc.z = fmaf(wd, __bfloat162float(zr[2]), acc.z); acc.w = fmaf(wd, __bfloat162float(zr[3]), acc.w);
+  }
+  const float g = grad_out ? *grad_out : 1.0f;
+  acc.x *= g; acc.y *= g; acc.z *= g; acc.w *= g;
+  if constexpr (sizeof(TO) == 4) {
+    *reinterpret_cast<float4*>(out + (int64_t)lr * TD + 4 * c4) = acc;
+  } else {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(acc.x, acc.y), p1 = __floats2bfloat162_rn(acc.z, acc.w);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&p0); w.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(out + (int64_t)lr * TD + 4 * c4) = w;
+  }
+}
+
+int choose_splits(int row_blocks, int col_tiles, int num_sms) {
+  // enough CTAs for ~7 waves so the tail is small, but at least 8 column tiles per CTA
+  int target = 7 * num_sms;
+  int s = (target + row_blocks - 1) / row_blocks;
+  int max_s = col_tiles / 8 > 0 ? col_tiles / 8 : 1;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return s;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+// ---- workspace layout shared by forward and backward ----
+TcPlan tc_plan(const supcon_problem_t* p) {
+  TcPlan pl;
+  pl.n_pad = (int)align_up((size_t)p->n_total, 128);
+  pl.rows_pad = (int)align_up((size_t)p->n_rows, 128);
+  pl.row_blocks = pl.rows_pad / 128;
+  pl.fwd_col_tiles = pl.n_pad / 128;
+  pl.bwd_col_tiles = (p->n_total + 63) / 64;
+  pl.fwd_splits = choose_splits(pl.row_blocks, pl.fwd_col_tiles, num_sms());
+  pl.bwd_splits = choose_splits(pl.row_blocks, pl.bwd_col_tiles / 2, num_sms());
+  pl.merge_blocks = pl.rows_pad / 128;
+  size_t off = 256;
+  pl.off_block_partials = off; off += align_up((size_t)pl.merge_blocks * SUPCON_N_PARTIALS * sizeof(double), 256);
+  pl.off_lab = off; off += align_up((size_t)pl.n_pad * 4, 256);
+  pl.off_nrm = off; off += align_up((size_t)pl.n_pad * 4, 256);
+  pl.off_colA = off; off += align_up((size_t)pl.n_pad * 4, 256);
+  pl.off_colAm = off; off += align_up((size_t)pl.n_pad * 4, 256);
+  pl.off_colB = off; off += align_up((size_t)pl.n_pad * 4, 256);
+  pl.off_colThr = off; off += align_up((size_t)pl.n_pad * 4, 256);
+  pl.off_colThrIdx = off; off += align_up((size_t)pl.n_pad * 4, 256);
+  pl.off_scalars = off; off += 256;
+  pl.off_part = off;
+  size_t fwd_part = (size_t)pl.fwd_splits * pl.rows_pad * 4 * sizeof(float);
+  size_t bwd_part = (size_t)pl.bwd_splits * pl.rows_pad * TD * sizeof(float);
+  off += align_up(fwd_part > bwd_part ? fwd_part : bwd_part, 256);
+  pl.total_bytes = off;
+  return pl;
+}
+
+bool tc_supported(const supcon_problem_t* p) {
+  if (p->z_dtype != SUPCON_BF16 || p->d != TD) return false;
+  if (!(p->tau >= 0.025f)) return false;
+  if (p->alpha != 0.f && p->topk >= 1) return false;   // hard-negative mining: exact path for now
+  if (p->n_total < 256) return false;
+  return true;
+}
+
+template <int SIM, bool UNI>
+static cudaError_t launch_fwd(const CUtensorMap& tm, const TcFwdArgs& a, int ctas, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<SIM, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tc_fwd_kernel<SIM, UNI><<<ctas, NTHREADS, smem, st>>>(tm, a);
+  return cudaGetLastError();
+}
+
+int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, float* row_stats,
+               double* partials, float* loss_out, void* workspace, cudaStream_t stream, const char** err) {
+  const TcPlan pl = tc_plan(p);
+  char* ws = reinterpret_cast<char*>(workspace);
+  CUtensorMap tm;
+  if (make_bf16_rowmajor_tmap(&tm, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 128) != 0) {
+    *err = "cuTensorMapEncodeTiled failed (z must be 16-byte aligned)";
+    return SUPCON_E_INVALID;
+  }
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 256, stream);
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  const bool uni = p->lambda_uni > 0.f;
+  {
+    int threads = 256, warps_per_block = threads / 32;
+    int blocks = (pl.n_pad + warps_per_block - 1) / warps_per_block;
+    tc_prep_fwd_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all,
+                                                       p->n_total, pl.n_pad, p->d,
+                                                       reinterpret_cast<int32_t*>(ws + pl.off_lab),
+                                                       reinterpret_cast<float*>(ws + pl.off_nrm), uni ? 1 : 0);
+  }
+  TcFwdArgs a;
+  a.lab_pad = reinterpret_cast<const int32_t*>(ws + pl.off_lab);
+  a.nrm_pad = reinterpret_cast<const float*>(ws + pl.off_nrm);
+  a.part = reinterpret_cast<float*>(ws + pl.off_part);
+  a.n_total = p->n_total; a.n_pad = pl.n_pad; a.row_offset = p->row_offset; a.n_rows = p->n_rows;
+  a.rows_pad = pl.rows_pad; a.splits = pl.fwd_splits; a.col_tiles = pl.fwd_col_tiles; a.topk = p->topk;
+  a.inv_tau = 1.0f / p->tau;
+  a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
+  const size_t smem = 3 * (size_t)NBOX * 128 * 128 + 1024;
+  const int ctas = pl.row_blocks * pl.fwd_splits;
+  const bool geo = p->similarity == SUPCON_GEODESIC;
+  if (geo && uni) e = launch_fwd<SUPCON_GEODESIC, true>(tm, a, ctas, smem, stream);
+  else if (geo) e = launch_fwd<SUPCON_GEODESIC, false>(tm, a, ctas, smem, stream);
+  else if (uni) e = launch_fwd<SUPCON_COSINE, true>(tm, a, ctas, smem, stream);
+  else e = launch_fwd<SUPCON_COSINE, false>(tm, a, ctas, smem, stream);
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  FinishArgs f{reinterpret_cast<double*>(ws + pl.off_block_partials), reinterpret_cast<unsigned*>(ws), partials,
+               loss_out, p->n_total, p->tau, p->alpha, p->lambda_uni, p->uni_t};
+  tc_fwd_merge_kernel<<<pl.merge_blocks, 128, 0, stream>>>(a, f, row_stats);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  return 0;
+}
+
+template <int SIM, bool UNI>
+static cudaError_t launch_bwd(const CUtensorMap& tmI, const CUtensorMap& tmJ, const TcBwdArgs& a, int ctas, size_t smem,
+                              cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<SIM, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tc_bwd_kernel<SIM, UNI><<<ctas, NTHREADS, smem, st>>>(tmI, tmJ, a);
+  return cudaGetLastError();
+}
+
+int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, const float* stats_all,
+                const double* partials_global, const float* grad_out, void* dz_out, int dz_dtype, void* workspace,
+                cudaStream_t stream, const char** err) {
+  const TcPlan pl = tc_plan(p);
+  char* ws = reinterpret_cast<char*>(workspace);
+  CUtensorMap tmI, tmJ;
+  if (make_bf16_rowmajor_tmap(&tmI, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 128) != 0 ||
+      make_bf16_rowmajor_tmap(&tmJ, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 64) != 0) {
+    *err = "cuTensorMapEncodeTiled failed (z must be 16-byte aligned)";
+    return SUPCON_E_INVALID;
+  }
+  const bool uni = p->lambda_uni > 0.f;
+  cudaError_t e;
+  if (uni) {  // squared norms (labels are re-copied by the bwd prep below)
+    int threads = 256, blocks = (pl.n_pad + 7) / 8;
+    tc_prep_fwd_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all,
+                                                       p->n_total, pl.n_pad, p->d,
+                                                       reinterpret_cast<int32_t*>(ws + pl.off_lab),
+                                                       reinterpret_cast<float*>(ws + pl.off_nrm), 1);
+  }
+  TcBwdPrepArgs pa;
+  pa.stats_all = stats_all; pa.partials = partials_global; pa.labels = labels_all;
+  pa.colA = reinterpret_cast<float*>(ws + pl.off_colA); pa.colAm = reinterpret_cast<float*>(ws + pl.off_colAm);
+  pa.colB = reinterpret_cast<float*>(ws + pl.off_colB); pa.colThr = reinterpret_cast<float*>(ws + pl.off_colThr);
+  pa.colThrIdx = reinterpret_cast<int32_t*>(ws + pl.off_colThrIdx);
+  pa.lab_pad = reinterpret_cast<int32_t*>(ws + pl.off_lab);
+  pa.scalars = reinterpret_cast<float*>(ws + pl.off_scalars);
+  pa.n_total = p->n_total; pa.n_pad = pl.n_pad; pa.topk = p->topk;
+  pa.tau = p->tau; pa.alpha = p->alpha; pa.lambda_uni = p->lambda_uni; pa.uni_t = p->uni_t;
+  tc_prep_bwd_kernel<<<(pl.n_pad + 255) / 256, 256, 0, stream>>>(pa);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+
+  TcBwdArgs a;
+  a.lab_pad = pa.lab_pad; a.nrm_pad = reinterpret_cast<const float*>(ws + pl.off_nrm);
+  a.colA = pa.colA; a.colB = pa.colB;
+  a.dz_part = reinterpret_cast<float*>(ws + pl.off_part);
+  a.n_total = p->n_total; a.n_pad = pl.n_pad; a.row_offset = p->row_offset; a.n_rows = p->n_rows;
+  a.rows_pad = pl.rows_pad; a.splits = pl.bwd_splits; a.col_tiles = pl.bwd_col_tiles;
+  a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
+  a.scalars = pa.scalars;
+  const size_t smem = (size_t)NBOX * 128 * 128 + 3 * (size_t)NBOX * 64 * 128 + 2 * 128 * 64 * 2 + 1024;
+  const int ctas = pl.row_blocks * pl.bwd_splits;
+  const bool geo = p->similarity == SUPCON_GEODESIC;
+  if (geo && uni) e = launch_bwd<SUPCON_GEODESIC, true>(tmI, tmJ, a, ctas, smem, stream);
+  else if (geo) e = launch_bwd<SUPCON_GEODESIC, false>(tmI, tmJ, a, ctas, smem, stream);
+  else if (uni) e = launch_bwd<SUPCON_COSINE, true>(tmI, tmJ, a, ctas, smem, stream);
+  else e = launch_bwd<SUPCON_COSINE, false>(tmI, tmJ, a, ctas, smem, stream);
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  const int64_t n4 = (int64_t)p->n_rows * (TD / 4);
+  const int blocks = (int)((n4 + 255) / 256);
+  if (dz_dtype == SUPCON_BF16)
+    tc_bwd_reduce_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<const __nv_bfloat16*>(z_all),
+                                                                    stats_all, grad_out,
+                                                                    reinterpret_cast<__nv_bfloat16*>(dz_out));
+  else
+    tc_bwd_reduce_kernel<float><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<const __nv_bfloat16*>(z_all), stats_all,
+                                                            grad_out, reinterpret_cast<float*>(dz_out));
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  return 0;
+}
+
+}  // namespace supcon
