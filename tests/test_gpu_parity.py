@@ -250,3 +250,87 @@ def test_training_step_reduces_loss(cuda_device):
         first = float(loss) if first is None else first
         last = float(loss)
     assert last < first - 0.05
+
+
+# ---------------------------------------------------------------------------
+# bf16 tensor-core path (tcgen05 / TMEM / TMA).  Oracle semantics for bf16:
+# the reference algorithm applied to z_bf16.float(); tolerance 2e-3 (north_star).
+# ---------------------------------------------------------------------------
+TC_CASES = [
+    # n, kind, classes, sim, tau, lam
+    (512, "iso", 2, "cosine", 0.07, 0.0),
+    (1000, "iso", 3, "cosine", 0.07, 0.0),          # ragged N: masked tail tile
+    (640, "clustered", 2, "cosine", 0.1, 0.05),
+    (512, "iso", 2, "geodesic", 0.07, 0.0),
+    (777, "iso", 5, "geodesic", 0.1, 0.2),
+    (2048, "iso", 2, "cosine", 0.03, 0.0),
+]
+
+
+@pytest.mark.parametrize("n,kind,classes,sim,tau,lam", TC_CASES)
+@pytest.mark.parametrize("flags", [2, 2 | 8, 2 | 16])   # tensor path both ways / forward only / backward only
+def test_tensor_core_path_bf16(cuda_device, n, kind, classes, sim, tau, lam, flags):
+    from wav2vec_contr_loss_b200 import functional as Fn
+    x, y = O.make_inputs(n, 256, kind, classes=classes)
+    zb = F.normalize(x, dim=1).to(torch.bfloat16)
+    kw = dict(tau=tau, similarity=sim, lam=lam, t=2.0, topk=15, alpha=0.0)
+    ref = G.oracle_for(zb.float(), y, **kw)
+    out = G.kernel_stats(zb, y, dtype=torch.bfloat16, flags=flags, **kw)
+    assert float(out["loss"]) == pytest.approx(ref["loss"], rel=TOL_BF16)
+    st = out["stats"].cpu()
+    assert float((st[:, 0].double() - ref["stats"]["lse"]).abs().max()) < 1e-4
+    assert bool((st.view(torch.int32)[:, 2].long() == ref["stats"]["npos"]).all())
+    dz = Fn.backward_rows(out["z"], out["y"], out["stats"], out["partials"], None, out["prob"],
+                          out_dtype=torch.float32)
+    assert G.rel_err(dz.cpu(), ref["dz"]) < TOL_BF16
+
+
+def test_tensor_core_path_through_module(cuda_device):
+    """bf16 z through the drop-in class takes the tensor path by default; grad_out scaling."""
+    x, y = O.make_inputs(1024, 256, "iso")
+    zb = F.normalize(x, dim=1).to(torch.bfloat16)
+    loss, dz = G.kernel_loss_and_grad(zb, y, tau=0.07, similarity="cosine", topk=15, alpha=0.0,
+                                      dtype=torch.bfloat16, grad_scale=3.0)
+    ref = G.oracle_for(zb.float(), y, tau=0.07, similarity="cosine", topk=15, alpha=0.0)
+    assert loss == pytest.approx(ref["loss"], rel=TOL_BF16)
+    assert G.rel_err(dz, ref["dz"]) < 2 * TOL_BF16      # dz additionally rounded to bf16 by autograd
+
+
+def test_tensor_core_row_blocks_compose(cuda_device):
+    """Row-sharded use of the tensor path: two ranks' row blocks == whole batch."""
+    from wav2vec_contr_loss_b200 import functional as Fn
+    x, y = O.make_inputs(1024, 256, "iso", classes=3)
+    zb = F.normalize(x, dim=1).to(torch.bfloat16)
+    kw = dict(tau=0.07, similarity="cosine", lam=0.05, t=2.0, topk=15, alpha=0.0)
+    a = G.kernel_stats(zb, y, dtype=torch.bfloat16, flags=2, row_offset=0, n_rows=384, **kw)
+    b = G.kernel_stats(zb, y, dtype=torch.bfloat16, flags=2, row_offset=384, n_rows=640, **kw)
+    partials = a["partials"] + b["partials"]
+    stats = torch.cat([a["stats"], b["stats"]])
+    whole = Fn.make_problem(1024, 256, 1, tau=0.07, similarity=0, lambda_uni=0.05, uni_t=2.0, topk=15, alpha=0.0)
+    ref = G.oracle_for(zb.float(), y, **kw)
+    assert float(Fn.finalize(whole, partials)) == pytest.approx(ref["loss"], rel=TOL_BF16)
+    dz_b = Fn.backward_rows(b["z"], b["y"], stats, partials, None, b["prob"], out_dtype=torch.float32)
+    assert G.rel_err(dz_b.cpu(), ref["dz"][384:]) < TOL_BF16
+
+
+def test_large_batch_properties_bf16(cuda_device):
+    """N = 16384 on the tensor path: loss against the row-blocked fp64 oracle, a sample of
+    dz rows against brute force, and permutation equivariance of the gradient."""
+    from wav2vec_contr_loss_b200 import functional as Fn
+    n = 16384
+    x, y = O.make_inputs(n, 256, "iso")
+    zb = F.normalize(x, dim=1).to(torch.bfloat16)
+    kw = dict(tau=0.07, similarity="cosine", lam=0.0, t=2.0, topk=15, alpha=0.0)
+    out = G.kernel_stats(zb, y, dtype=torch.bfloat16, flags=2, **kw)
+    dz = Fn.backward_rows(out["z"], out["y"], out["stats"], out["partials"], None, out["prob"],
+                          out_dtype=torch.float32).cpu()
+    ref = O.closed_form(zb.float(), y, temperature=0.07, similarity="cosine", topk_neg=15, alpha=0.0,
+                        dtype=torch.float32, block=2048)
+    assert float(out["loss"]) == pytest.approx(ref["loss"], rel=1e-4)
+    assert G.rel_err(dz, ref["dz"]) < TOL_BF16
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(3))
+    out_p = G.kernel_stats(zb[perm], y[perm], dtype=torch.bfloat16, flags=2, **kw)
+    dz_p = Fn.backward_rows(out_p["z"], out_p["y"], out_p["stats"], out_p["partials"], None, out_p["prob"],
+                            out_dtype=torch.float32).cpu()
+    assert float(out_p["loss"]) == pytest.approx(float(out["loss"]), rel=1e-5)
+    assert G.rel_err(dz_p, dz[perm]) < TOL_BF16

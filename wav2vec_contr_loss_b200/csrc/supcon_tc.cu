@@ -129,14 +129,15 @@ struct RowSums {
 
 template <int SIM, bool UNI, bool MASKED>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int gi, int n_total, int lab_r,
-                                          float nrm_r, const int32_t* __restrict__ lab_pad,
-                                          const float* __restrict__ nrm_pad, float c1, float c0, float ut2,
+                                          float nrm_r, const int32_t* __restrict__ lab_s,
+                                          const float* __restrict__ nrm_s, float c1, float c0, float ut2,
                                           RowSums& st) {
+  // lab_s / nrm_s: this chunk's 32 column labels / squared norms in shared memory (broadcast reads)
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const int4 lb = __ldg(reinterpret_cast<const int4*>(lab_pad + gj0 + 4 * q));
+    const int4 lb = *reinterpret_cast<const int4*>(lab_s + 4 * q);
     float4 nj = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (UNI) nj = __ldg(reinterpret_cast<const float4*>(nrm_pad + gj0 + 4 * q));
+    if (UNI) nj = *reinterpret_cast<const float4*>(nrm_s + 4 * q);
     const int labs[4] = {lb.x, lb.y, lb.z, lb.w};
     const float njs[4] = {nj.x, nj.y, nj.z, nj.w};
 #pragma unroll
@@ -175,9 +176,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sZI = smem;
   unsigned char* sZJ = smem + TILE_BYTES;
-  __shared__ __align__(8) uint64_t bar_zi, bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+  constexpr int RING = 4;  // column label/norm slots: slot t%4 is rewritten only after softmax(t) is done
+  __shared__ __align__(8) uint64_t bar_zi, bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2],
+      bar_col[RING];
   __shared__ uint32_t tmem_base_s;
   __shared__ float comb[TBM][4];
+  __shared__ __align__(16) int32_t lab_ring[RING][BN];
+  __shared__ __align__(16) float nrm_ring[UNI ? RING : 1][BN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rb = blockIdx.x / a.splits, split = blockIdx.x % a.splits;
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
     ptx::mbar_init(&bar_zi, 1);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_tfull[b], 1); ptx::mbar_init(&bar_tempty[b], 128); }
+    for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
     ptx::fence_mbar_init();
     ptx::tma_prefetch_desc(&tmap);
   }
@@ -200,17 +206,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (lane 0) + column label/norm staging (all lanes) =====
     if (lane == 0) {
       ptx::mbar_expect_tx(&bar_zi, TILE_BYTES);
       for (int b = 0; b < NBOX; ++b) ptx::tma_load_2d(sZI + b * BOX_BYTES, &tmap, &bar_zi, 64 * b, row0);
-      for (int t = 0; t < ntiles; ++t) {
-        const int st = t % STAGES, use = t / STAGES;
-        ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
+    }
+    for (int t = 0; t < ntiles; ++t) {
+      const int st = t % STAGES, use = t / STAGES, slot = t % RING;
+      const int col0 = (ct_begin + t) * BN;
+      // waiting for the smem stage of tile t-2 also guarantees softmax(t-4) has finished with this slot
+      ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
+      if (lane == 0) {
         ptx::mbar_expect_tx(&bar_full[st], TILE_BYTES);
         for (int b = 0; b < NBOX; ++b)
-          ptx::tma_load_2d(sZJ + st * TILE_BYTES + b * BOX_BYTES, &tmap, &bar_full[st], 64 * b, (ct_begin + t) * BN);
+          ptx::tma_load_2d(sZJ + st * TILE_BYTES + b * BOX_BYTES, &tmap, &bar_full[st], 64 * b, col0);
       }
+      *reinterpret_cast<int4*>(&lab_ring[slot][4 * lane]) =
+          __ldg(reinterpret_cast<const int4*>(a.lab_pad + col0 + 4 * lane));
+      if (UNI)
+        *reinterpret_cast<float4*>(&nrm_ring[slot][4 * lane]) =
+            __ldg(reinterpret_cast<const float4*>(a.nrm_pad + col0 + 4 * lane));
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar_col[slot]);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -244,23 +261,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
     RowSums st;
     st.sum_all = 0.f; st.sum_pos_s = 0.f; st.wsum = 0.f; st.npos = 0;
     for (int t = wg; t < ntiles; t += 2) {
-      const int buf = wg, buse = t >> 1;
+      const int buf = wg, buse = t >> 1, slot = t % RING;
       const int col0 = (ct_begin + t) * BN;
+      ptx::mbar_wait(&bar_col[slot], (t / RING) & 1);
       ptx::mbar_wait(&bar_tfull[buf], buse & 1);
       ptx::tc_fence_after_sync();
       const bool masked = (col0 + BN > a.n_total) || (col0 < row0 + TBM && row0 < col0 + BN);
       const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + buf * BN;
-#pragma unroll 1
+      const int32_t* lab_s = lab_ring[slot];
+      const float* nrm_s = nrm_ring[UNI ? slot : 0];
+      uint32_t ra[32], rb2[32];
+      ptx::tmem_ld32(taddr, ra);
+      ptx::tmem_ld_wait();
+#pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld32(taddr + 32 * c, r);
-        ptx::tmem_ld_wait();
+        // software pipeline: fetch chunk c+1 from TMEM while chunk c is processed
+        uint32_t (&cur)[32] = (c & 1) ? rb2 : ra;
+        uint32_t (&nxt)[32] = (c & 1) ? ra : rb2;
+        if (c + 1 < BN / 32) ptx::tmem_ld32(taddr + 32 * (c + 1), nxt);
         if (masked)
-          fwd_chunk<SIM, UNI, true>(r, col0 + 32 * c, gi, a.n_total, lab_r, nrm_r, a.lab_pad, a.nrm_pad, a.c1, a.c0,
-                                    a.ut2, st);
+          fwd_chunk<SIM, UNI, true>(cur, col0 + 32 * c, gi, a.n_total, lab_r, nrm_r, lab_s + 32 * c, nrm_s + 32 * c,
+                                    a.c1, a.c0, a.ut2, st);
         else
-          fwd_chunk<SIM, UNI, false>(r, col0 + 32 * c, gi, a.n_total, lab_r, nrm_r, a.lab_pad, a.nrm_pad, a.c1, a.c0,
-                                     a.ut2, st);
+          fwd_chunk<SIM, UNI, false>(cur, col0 + 32 * c, gi, a.n_total, lab_r, nrm_r, lab_s + 32 * c, nrm_s + 32 * c,
+                                     a.c1, a.c0, a.ut2, st);
+        if (c + 1 < BN / 32) ptx::tmem_ld_wait();
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&bar_tempty[buf]);
@@ -324,16 +349,22 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
 // ---------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------
+struct ColVecs {  // this chunk's 32 column entries in shared memory
+  const int32_t* lab;
+  const float *A, *B, *nrm;
+};
+
 template <int SIM, bool UNI, bool MASKED>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw)[16], int gj0, int gi, int lab_r,
-                                          float A_r, float B_r, float nrm_r, float cu, const TcBwdArgs& a) {
+                                          float A_r, float B_r, float nrm_r, float cu, const ColVecs& cv,
+                                          const TcBwdArgs& a) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const int4 lb = __ldg(reinterpret_cast<const int4*>(a.lab_pad + gj0 + 4 * q));
-    const float4 Aj = __ldg(reinterpret_cast<const float4*>(a.colA + gj0 + 4 * q));
-    const float4 Bj = __ldg(reinterpret_cast<const float4*>(a.colB + gj0 + 4 * q));
+    const int4 lb = *reinterpret_cast<const int4*>(cv.lab + 4 * q);
+    const float4 Aj = *reinterpret_cast<const float4*>(cv.A + 4 * q);
+    const float4 Bj = *reinterpret_cast<const float4*>(cv.B + 4 * q);
     float4 nj = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (UNI) nj = __ldg(reinterpret_cast<const float4*>(a.nrm_pad + gj0 + 4 * q));
+    if (UNI) nj = *reinterpret_cast<const float4*>(cv.nrm + 4 * q);
     const int labs[4] = {lb.x, lb.y, lb.z, lb.w};
     const float As[4] = {Aj.x, Aj.y, Aj.z, Aj.w};
     const float Bs[4] = {Bj.x, Bj.y, Bj.z, Bj.w};
@@ -375,8 +406,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   unsigned char* sZJ = sZI + TILEI_BYTES;
   unsigned char* sH = sZJ + STAGES * TILEJ_BYTES;
   __shared__ __align__(8) uint64_t bar_zi, bar_full[STAGES], bar_empty[STAGES], bar_sfull[2], bar_sempty[2],
-      bar_hfull[2], bar_hempty[2], bar_done;
+      bar_hfull[2], bar_hempty[2], bar_done, bar_col[4];
   __shared__ uint32_t tmem_base_s;
+  constexpr int RING = 4;  // column-vector slots; slot t%4 is rewritten only after H(t) has been formed
+  __shared__ __align__(16) int32_t lab_ring[RING][BN];
+  __shared__ __align__(16) float colA_ring[RING][BN], colB_ring[RING][BN];
+  __shared__ __align__(16) float nrm_ring[UNI ? RING : 1][BN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rb = blockIdx.x / a.splits, split = blockIdx.x % a.splits;
@@ -388,6 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   if (tid == 0) {
     ptx::mbar_init(&bar_zi, 1);
     ptx::mbar_init(&bar_done, 1);
+    for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_sempty[b], 256);
@@ -404,18 +440,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (lane 0) + column-vector staging (all lanes) =====
     if (lane == 0) {
       ptx::mbar_expect_tx(&bar_zi, TILEI_BYTES);
       for (int b = 0; b < NBOX; ++b) ptx::tma_load_2d(sZI + b * BOXI_BYTES, &tmapI, &bar_zi, 64 * b, row0);
-      for (int t = 0; t < ntiles; ++t) {
-        const int st = t % STAGES, use = t / STAGES;
-        ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
+    }
+    for (int t = 0; t < ntiles; ++t) {
+      const int st = t % STAGES, use = t / STAGES, slot = t % RING;
+      const int col0 = (ct_begin + t) * BN;
+      // stage st was last used by tile t-3; its release (dZ(t-3) complete) implies H(t-4) was formed long ago
+      ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
+      if (lane == 0) {
         ptx::mbar_expect_tx(&bar_full[st], TILEJ_BYTES);
         for (int b = 0; b < NBOX; ++b)
-          ptx::tma_load_2d(sZJ + st * TILEJ_BYTES + b * BOXJ_BYTES, &tmapJ, &bar_full[st], 64 * b,
-                           (ct_begin + t) * BN);
+          ptx::tma_load_2d(sZJ + st * TILEJ_BYTES + b * BOXJ_BYTES, &tmapJ, &bar_full[st], 64 * b, col0);
       }
+      if (lane < 16) {
+        *reinterpret_cast<int4*>(&lab_ring[slot][4 * lane]) =
+            __ldg(reinterpret_cast<const int4*>(a.lab_pad + col0 + 4 * lane));
+        *reinterpret_cast<float4*>(&colA_ring[slot][4 * lane]) =
+            __ldg(reinterpret_cast<const float4*>(a.colA + col0 + 4 * lane));
+      } else {
+        const int l = lane - 16;
+        *reinterpret_cast<float4*>(&colB_ring[slot][4 * l]) =
+            __ldg(reinterpret_cast<const float4*>(a.colB + col0 + 4 * l));
+        if (UNI)
+          *reinterpret_cast<float4*>(&nrm_ring[slot][4 * l]) =
+              __ldg(reinterpret_cast<const float4*>(a.nrm_pad + col0 + 4 * l));
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar_col[slot]);
     }
   } else if (warp == 1) {
     // ===== MMA issuer: iteration t issues S(t) and then dZ(t-1) =====
@@ -470,8 +524,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
     const float cu = UNI ? a.scalars[0] : 0.f;
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     for (int t = 0; t < ntiles; ++t) {
-      const int buf = t & 1, buse = t >> 1;
+      const int buf = t & 1, buse = t >> 1, slot = t % RING;
       const int col0 = (ct_begin + t) * BN;
+      ColVecs cv;
+      cv.lab = lab_ring[slot] + 32 * wg; cv.A = colA_ring[slot] + 32 * wg; cv.B = colB_ring[slot] + 32 * wg;
+      cv.nrm = nrm_ring[UNI ? slot : 0] + 32 * wg;
+      ptx::mbar_wait(&bar_col[slot], (t / RING) & 1);
       ptx::mbar_wait(&bar_sfull[buf], buse & 1);
       ptx::tc_fence_after_sync();
       uint32_t r[32];
@@ -481,8 +539,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       ptx::mbar_arrive(&bar_sempty[buf]);
       uint32_t hw[16];
       const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
-      if (masked) bwd_chunk<SIM, UNI, true>(r, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, a);
-      else bwd_chunk<SIM, UNI, false>(r, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, a);
+      if (masked) bwd_chunk<SIM, UNI, true>(r, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, cv, a);
+      else bwd_chunk<SIM, UNI, false>(r, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, cv, a);
       ptx::mbar_wait(&bar_hempty[buf], (buse & 1) ^ 1);
       const uint32_t hbase = ptx::smem_u32(sH + buf * H_BYTES) + lrow * 128;
 #pragma unroll
