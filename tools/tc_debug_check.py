@@ -12,11 +12,14 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 n = 512
 z = torch.nn.functional.normalize(torch.randn(n, 256), dim=1).to(dev).to(torch.bfloat16)
-for (ri, rj) in [(0, 0), (128, 256), (384, 128), (448, 64)]:
+TS = 1 << 24
+for (ri, rj) in [(0, 0), (128, 256), (384, 128), (448, 64), (TS + 0, 0), (TS + 128, 256), (TS + 448, 64)]:
     s = torch.full((128, 128), float("nan"), device=dev)
     o = torch.full((128, 256), float("nan"), device=dev)
     _cabi.check(lib.supcon_debug_tc_tile(_p(z), n, 256, ri, rj, _p(s), _p(o), _stream(dev)), "debug")
     torch.cuda.synchronize()
+    mode = "TS" if ri >= TS else "SS"
+    ri = ri % TS
     zi, zj = torch.zeros(128, 256, device=dev), torch.zeros(128, 256, device=dev)
     a = z[ri:ri + 128].float(); b = z[rj:rj + 128].float()
     zi[: a.size(0)] = a; zj[: b.size(0)] = b
@@ -24,7 +27,7 @@ for (ri, rj) in [(0, 0), (128, 256), (384, 128), (448, 64)]:
     o_ref = s.to(torch.bfloat16).double() @ zj.double()
     es = (s.double() - s_ref).abs().max().item()
     eo = (o.double() - o_ref).abs().max().item()
-    print(f"tile ({ri},{rj}): max|S-ref|={es:.3e} (|S|max {s_ref.abs().max():.3f})  max|O-ref|={eo:.3e} (|O|max {o_ref.abs().max():.3f})")
+    print(f"{mode} tile ({ri},{rj}): max|S-ref|={es:.3e} (|S|max {s_ref.abs().max():.3f})  max|O-ref|={eo:.3e} (|O|max {o_ref.abs().max():.3f})")
     if not (es < 1e-5):
         bad = (s.double() - s_ref).abs() > 1e-5
         print("  S mismatch count", int(bad.sum()), "first rows", bad.any(1).nonzero()[:8].flatten().tolist(),
