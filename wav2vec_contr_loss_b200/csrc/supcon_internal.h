@@ -32,7 +32,7 @@ cudaError_t ffma_topk_indices(const FfmaArgs& a, int32_t* idx_out, cudaStream_t 
 
 // ---- bf16 tensor-core path (supcon_tc.cu) ----
 struct TcPlan {
-  int n_pad, rows_pad, row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_splits, bwd_splits, merge_blocks;
+  int n_pad, rows_pad, row_blocks, fwd_row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_splits, bwd_splits, merge_blocks;
   size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
       off_scalars, off_part, total_bytes;
 };

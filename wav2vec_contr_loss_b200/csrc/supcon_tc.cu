@@ -166,40 +166,65 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
   }
 }
 
+// Z rows -> tensor memory as the A operand of tcgen05.mma (kind::f16, A from TMEM):
+// lane = row, 32-bit column m holds the bf16 pair (z[2m], z[2m+1]).
+__device__ __forceinline__ void load_rows_to_tmem(const __nv_bfloat16* __restrict__ z, int gi, int n_total,
+                                                  uint32_t taddr) {
+  const uint4* src = reinterpret_cast<const uint4*>(z + (int64_t)min(gi, n_total - 1) * TD);
+#pragma unroll 1
+  for (int c = 0; c < TD / 64; ++c) {
+    uint32_t w[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint4 v = (gi < n_total) ? __ldg(src + 8 * c + q) : make_uint4(0u, 0u, 0u, 0u);
+      w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+    ptx::tmem_st32(taddr + 32 * c, w);
+  }
+  ptx::tmem_st_wait();
+}
+
+// Forward: one CTA owns TWO 128-row blocks (a, b) that share every Z_J tile, so each
+// byte staged by TMA feeds two MMAs (halves the shared-memory traffic per flop); the
+// row blocks live in tensor memory as the MMA A operands.  Warpgroup g drains S_g:
+// it pulls the whole 128x128 tile into registers, releases the TMEM buffer at once
+// (the next MMA into it overlaps the exp work) and then reduces from registers.
 template <int SIM, bool UNI>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                             const __nv_bfloat16* __restrict__ z, TcFwdArgs a) {
   constexpr int BN = 128;
-  constexpr uint32_t BOX_BYTES = 128 * 128;         // 128 rows x 128 B
+  constexpr uint32_t BOX_BYTES = 128 * 128;          // 128 rows x 128 B
   constexpr uint32_t TILE_BYTES = NBOX * BOX_BYTES;  // 64 KB
-  constexpr int STAGES = 2;
+  constexpr int STAGES = 3;
+  constexpr uint32_t TM_A = 0, TM_S = 256;           // A_g at 128 g, S_g at 256 + 128 g
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* sZI = smem;
-  unsigned char* sZJ = smem + TILE_BYTES;
-  constexpr int RING = 4;  // column label/norm slots: slot t%4 is rewritten only after softmax(t) is done
-  __shared__ __align__(8) uint64_t bar_zi, bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2],
+  unsigned char* sZJ = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  // Column label/norm slots.  The producer may write the slot of tile t once the MMAs of tile t-3 are done;
+  // those were issued after both warpgroups pulled tile t-4 into registers, i.e. after they finished
+  // reducing tile t-5 (they still read the slot of t-4 while reducing it) => at least 5 slots.
+  constexpr int RING = 8;
+  __shared__ __align__(8) uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2],
       bar_col[RING];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float comb[TBM][4];
   __shared__ __align__(16) int32_t lab_ring[RING][BN];
   __shared__ __align__(16) float nrm_ring[UNI ? RING : 1][BN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rb = blockIdx.x / a.splits, split = blockIdx.x % a.splits;
-  const int row0 = a.row_offset + rb * TBM;
+  const int row0 = a.row_offset + rb * (2 * TBM);
   const int ct_begin = (int)(((int64_t)a.col_tiles * split) / a.splits);
   const int ct_end = (int)(((int64_t)a.col_tiles * (split + 1)) / a.splits);
   const int ntiles = ct_end - ct_begin;
 
   if (tid == 0) {
-    ptx::mbar_init(&bar_zi, 1);
+    ptx::mbar_init(&bar_a, 256);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_tfull[b], 1); ptx::mbar_init(&bar_tempty[b], 128); }
     for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
     ptx::fence_mbar_init();
     ptx::tma_prefetch_desc(&tmap);
   }
-  if (warp == 1) ptx::tmem_alloc<256>(&tmem_base_s);
+  if (warp == 1) ptx::tmem_alloc<512>(&tmem_base_s);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -207,14 +232,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer (lane 0) + column label/norm staging (all lanes) =====
-    if (lane == 0) {
-      ptx::mbar_expect_tx(&bar_zi, TILE_BYTES);
-      for (int b = 0; b < NBOX; ++b) ptx::tma_load_2d(sZI + b * BOX_BYTES, &tmap, &bar_zi, 64 * b, row0);
-    }
     for (int t = 0; t < ntiles; ++t) {
       const int st = t % STAGES, use = t / STAGES, slot = t % RING;
       const int col0 = (ct_begin + t) * BN;
-      // waiting for the smem stage of tile t-2 also guarantees softmax(t-4) has finished with this slot
       ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
       if (lane == 0) {
         ptx::mbar_expect_tx(&bar_full[st], TILE_BYTES);
@@ -233,82 +253,80 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::idesc_bf16(128, BN, false, false);
-      const uint32_t a0 = ptx::smem_u32(sZI);
-      ptx::mbar_wait(&bar_zi, 0);
+      ptx::mbar_wait(&bar_a, 0);
       for (int t = 0; t < ntiles; ++t) {
-        const int st = t % STAGES, use = t / STAGES, buf = t & 1, buse = t >> 1;
+        const int st = t % STAGES, use = t / STAGES;
         ptx::mbar_wait(&bar_full[st], use & 1);
-        ptx::mbar_wait(&bar_tempty[buf], (buse & 1) ^ 1);
-        ptx::tc_fence_after_sync();
         const uint32_t b0 = ptx::smem_u32(sZJ + st * TILE_BYTES);
 #pragma unroll
-        for (int ks = 0; ks < TD / 16; ++ks) {
-          const uint32_t off = (ks >> 2) * BOX_BYTES + (ks & 3) * 32;
-          ptx::mma_ss(tmem + buf * BN, ptx::smem_desc_sw128(a0 + off, 16, 1024),
-                      ptx::smem_desc_sw128(b0 + off, 16, 1024), idesc, ks > 0);
+        for (int g = 0; g < 2; ++g) {
+          ptx::mbar_wait(&bar_tempty[g], (t & 1) ^ 1);
+          ptx::tc_fence_after_sync();
+#pragma unroll
+          for (int ks = 0; ks < TD / 16; ++ks) {
+            const uint32_t off = (ks >> 2) * BOX_BYTES + (ks & 3) * 32;
+            ptx::mma_ts(tmem + TM_S + g * BN, tmem + TM_A + g * (TD / 2) + 8 * ks,
+                        ptx::smem_desc_sw128(b0 + off, 16, 1024), idesc, ks > 0);
+          }
+          ptx::mma_commit(&bar_tfull[g]);
         }
         ptx::mma_commit(&bar_empty[st]);
-        ptx::mma_commit(&bar_tfull[buf]);
       }
     }
   } else {
-    // ===== softmax warpgroups: warps 2-5 drain buffer 0 (even tiles), warps 6-9 buffer 1 =====
+    // ===== softmax warpgroups: warps 2-5 own row block a, warps 6-9 row block b =====
     const int wg = (warp - 2) >> 2;
-    const int lrow = 32 * (warp & 3) + lane;  // TMEM lane == row of the block
-    const int gi = row0 + lrow;
+    const int lrow = 32 * (warp & 3) + lane;  // TMEM lane == row within the block
+    const int gi = row0 + wg * TBM + lrow;
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    load_rows_to_tmem(z, gi, a.n_total, tmem + lane_addr + TM_A + wg * (TD / 2));
+    ptx::tc_fence_before_sync();
+    ptx::mbar_arrive(&bar_a);
     const int lab_r = a.lab_pad[min(gi, a.n_pad - 1)];
     const float nrm_r = UNI ? a.nrm_pad[min(gi, a.n_pad - 1)] : 0.f;
+    const int rblk0 = row0 + wg * TBM;
     RowSums st;
     st.sum_all = 0.f; st.sum_pos_s = 0.f; st.wsum = 0.f; st.npos = 0;
-    for (int t = wg; t < ntiles; t += 2) {
-      const int buf = wg, buse = t >> 1, slot = t % RING;
+    const uint32_t taddr = tmem + lane_addr + TM_S + wg * BN;
+    for (int t = 0; t < ntiles; ++t) {
+      const int slot = t % RING;
       const int col0 = (ct_begin + t) * BN;
       ptx::mbar_wait(&bar_col[slot], (t / RING) & 1);
-      ptx::mbar_wait(&bar_tfull[buf], buse & 1);
+      ptx::mbar_wait(&bar_tfull[wg], t & 1);
       ptx::tc_fence_after_sync();
-      const bool masked = (col0 + BN > a.n_total) || (col0 < row0 + TBM && row0 < col0 + BN);
-      const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + buf * BN;
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      ptx::tmem_ld32(taddr, r0);
+      ptx::tmem_ld32(taddr + 32, r1);
+      ptx::tmem_ld32(taddr + 64, r2);
+      ptx::tmem_ld32(taddr + 96, r3);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&bar_tempty[wg]);   // S_g is free again: the next MMA overlaps the work below
+      const bool masked = (col0 + BN > a.n_total) || (col0 < rblk0 + TBM && rblk0 < col0 + BN);
       const int32_t* lab_s = lab_ring[slot];
       const float* nrm_s = nrm_ring[UNI ? slot : 0];
-      uint32_t ra[32], rb2[32];
-      ptx::tmem_ld32(taddr, ra);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        // software pipeline: fetch chunk c+1 from TMEM while chunk c is processed
-        uint32_t (&cur)[32] = (c & 1) ? rb2 : ra;
-        uint32_t (&nxt)[32] = (c & 1) ? ra : rb2;
-        if (c + 1 < BN / 32) ptx::tmem_ld32(taddr + 32 * (c + 1), nxt);
-        if (masked)
-          fwd_chunk<SIM, UNI, true>(cur, col0 + 32 * c, gi, a.n_total, lab_r, nrm_r, lab_s + 32 * c, nrm_s + 32 * c,
-                                    a.c1, a.c0, a.ut2, st);
-        else
-          fwd_chunk<SIM, UNI, false>(cur, col0 + 32 * c, gi, a.n_total, lab_r, nrm_r, lab_s + 32 * c, nrm_s + 32 * c,
-                                     a.c1, a.c0, a.ut2, st);
-        if (c + 1 < BN / 32) ptx::tmem_ld_wait();
+      if (masked) {
+        fwd_chunk<SIM, UNI, true>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st);
+        fwd_chunk<SIM, UNI, true>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st);
+        fwd_chunk<SIM, UNI, true>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st);
+        fwd_chunk<SIM, UNI, true>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st);
+      } else {
+        fwd_chunk<SIM, UNI, false>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st);
+        fwd_chunk<SIM, UNI, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st);
+        fwd_chunk<SIM, UNI, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st);
+        fwd_chunk<SIM, UNI, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st);
       }
-      ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&bar_tempty[buf]);
     }
-    if (wg == 1) {
-      comb[lrow][0] = st.sum_all; comb[lrow][1] = st.sum_pos_s; comb[lrow][2] = st.wsum;
-      comb[lrow][3] = __int_as_float(st.npos);
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (wg == 0 && gi < a.row_offset + a.n_rows) {
+    if (gi < a.row_offset + a.n_rows) {
       float* out = a.part + ((int64_t)split * a.rows_pad + (gi - a.row_offset)) * 4;
-      float4 v;
-      v.x = st.sum_all + comb[lrow][0];
-      v.y = st.sum_pos_s + comb[lrow][1];
-      v.z = st.wsum + comb[lrow][2];
-      v.w = __int_as_float(st.npos + __float_as_int(comb[lrow][3]));
-      *reinterpret_cast<float4*>(out) = v;
+      *reinterpret_cast<float4*>(out) = make_float4(st.sum_all, st.sum_pos_s, st.wsum, __int_as_float(st.npos));
     }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<256>(tmem);
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem);
 }
+
 
 // merge the column splits into row statistics + loss partial sums
 __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishArgs f, float* __restrict__ row_stats) {
@@ -389,26 +407,26 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw
   }
 }
 
+// Backward: one CTA owns a 128-row block; Z_I lives in tensor memory (A operand of the
+// S MMAs), the two warpgroups take alternate 64-column tiles: pull S(t) into registers,
+// form H(t) and write it back as packed bf16 over the first 32 columns of the same S
+// buffer, from where it is the A operand of dZ += H Z_J (no shared-memory round trip).
+// Tensor-pipe order: S(0) S(1) dZ(0) S(2) dZ(1) ...; tcgen05.mma executes in issue order,
+// so S(t+2) cannot overwrite the buffer dZ(t) is still reading.
 template <int SIM, bool UNI>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapI,
-                                                             const __grid_constant__ CUtensorMap tmapJ, TcBwdArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapJ,
+                                                             const __nv_bfloat16* __restrict__ z, TcBwdArgs a) {
   constexpr int BN = 64;
-  constexpr int STAGES = 3;
-  constexpr uint32_t BOXI_BYTES = 128 * 128;            // Z_I boxes: 128 rows
-  constexpr uint32_t TILEI_BYTES = NBOX * BOXI_BYTES;   // 64 KB
-  constexpr uint32_t BOXJ_BYTES = BN * 128;             // Z_J boxes: 64 rows
-  constexpr uint32_t TILEJ_BYTES = NBOX * BOXJ_BYTES;   // 32 KB
-  constexpr uint32_t H_BYTES = TBM * BN * 2;            // 16 KB
-  constexpr uint32_t TM_DZ = 0, TM_S = 256;             // TMEM columns: dZ [0,256), S buffers 256 + 64 b
+  constexpr int STAGES = 4;
+  constexpr int RING = STAGES;
+  constexpr uint32_t BOXJ_BYTES = BN * 128;            // Z_J boxes: 64 rows x 128 B
+  constexpr uint32_t TILEJ_BYTES = NBOX * BOXJ_BYTES;  // 32 KB
+  constexpr uint32_t TM_DZ = 0, TM_A = 256, TM_S = 384;  // dZ [0,256) | Z_I [256,384) | S buffers 384 + 64 b
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* sZI = smem;
-  unsigned char* sZJ = sZI + TILEI_BYTES;
-  unsigned char* sH = sZJ + STAGES * TILEJ_BYTES;
-  __shared__ __align__(8) uint64_t bar_zi, bar_full[STAGES], bar_empty[STAGES], bar_sfull[2], bar_sempty[2],
-      bar_hfull[2], bar_hempty[2], bar_done, bar_col[4];
+  unsigned char* sZJ = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_sfull[2], bar_hfull[2], bar_done,
+      bar_col[RING];
   __shared__ uint32_t tmem_base_s;
-  constexpr int RING = 4;  // column-vector slots; slot t%4 is rewritten only after H(t) has been formed
   __shared__ __align__(16) int32_t lab_ring[RING][BN];
   __shared__ __align__(16) float colA_ring[RING][BN], colB_ring[RING][BN];
   __shared__ __align__(16) float nrm_ring[UNI ? RING : 1][BN];
@@ -421,16 +439,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   const int ntiles = ct_end - ct_begin;
 
   if (tid == 0) {
-    ptx::mbar_init(&bar_zi, 1);
+    ptx::mbar_init(&bar_a, 128);
     ptx::mbar_init(&bar_done, 1);
-    for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_sempty[b], 256);
-      ptx::mbar_init(&bar_hfull[b], 256); ptx::mbar_init(&bar_hempty[b], 1);
-    }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_hfull[b], 128); }
+    for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
     ptx::fence_mbar_init();
-    ptx::tma_prefetch_desc(&tmapI);
     ptx::tma_prefetch_desc(&tmapJ);
   }
   if (warp == 1) ptx::tmem_alloc<512>(&tmem_base_s);
@@ -441,14 +455,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer (lane 0) + column-vector staging (all lanes) =====
-    if (lane == 0) {
-      ptx::mbar_expect_tx(&bar_zi, TILEI_BYTES);
-      for (int b = 0; b < NBOX; ++b) ptx::tma_load_2d(sZI + b * BOXI_BYTES, &tmapI, &bar_zi, 64 * b, row0);
-    }
     for (int t = 0; t < ntiles; ++t) {
       const int st = t % STAGES, use = t / STAGES, slot = t % RING;
       const int col0 = (ct_begin + t) * BN;
-      // stage st was last used by tile t-3; its release (dZ(t-3) complete) implies H(t-4) was formed long ago
+      // stage/slot st was last used by tile t-4; its release (dZ(t-4) complete) implies H(t-4) was formed
       ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
       if (lane == 0) {
         ptx::mbar_expect_tx(&bar_full[st], TILEJ_BYTES);
@@ -476,21 +486,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::idesc_bf16(128, BN, false, false);
       constexpr uint32_t idesc_dz = ptx::idesc_bf16(128, TD, false, true);
-      const uint32_t a0 = ptx::smem_u32(sZI);
-      ptx::mbar_wait(&bar_zi, 0);
+      ptx::mbar_wait(&bar_a, 0);
       for (int t = 0; t <= ntiles; ++t) {
         if (t < ntiles) {
-          const int st = t % STAGES, use = t / STAGES, buf = t & 1, buse = t >> 1;
+          const int st = t % STAGES, use = t / STAGES, buf = t & 1;
           ptx::mbar_wait(&bar_full[st], use & 1);
-          ptx::mbar_wait(&bar_sempty[buf], (buse & 1) ^ 1);
           ptx::tc_fence_after_sync();
           const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
 #pragma unroll
           for (int ks = 0; ks < TD / 16; ++ks) {
-            const uint32_t offa = (ks >> 2) * BOXI_BYTES + (ks & 3) * 32;
             const uint32_t offb = (ks >> 2) * BOXJ_BYTES + (ks & 3) * 32;
-            ptx::mma_ss(tmem + TM_S + buf * BN, ptx::smem_desc_sw128(a0 + offa, 16, 1024),
-                        ptx::smem_desc_sw128(b0 + offb, 16, 1024), idesc_s, ks > 0);
+            ptx::mma_ts(tmem + TM_S + buf * BN, tmem + TM_A + 8 * ks, ptx::smem_desc_sw128(b0 + offb, 16, 1024),
+                        idesc_s, ks > 0);
           }
           ptx::mma_commit(&bar_sfull[buf]);
         }
@@ -499,59 +506,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
           const int st = tt % STAGES, buf = tt & 1, buse = tt >> 1;
           ptx::mbar_wait(&bar_hfull[buf], buse & 1);
           ptx::tc_fence_after_sync();
-          const uint32_t h0 = ptx::smem_u32(sH + buf * H_BYTES);
           const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk) {
-            ptx::mma_ss(tmem + TM_DZ, ptx::smem_desc_sw128(h0 + kk * 32, 16, 1024),
+            ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + 8 * kk,
                         ptx::smem_desc_sw128(b0 + kk * 16 * 128, BOXJ_BYTES, 1024), idesc_dz, (tt > 0 || kk > 0));
           }
           ptx::mma_commit(&bar_empty[st]);
-          ptx::mma_commit(&bar_hempty[buf]);
         }
       }
       ptx::mma_commit(&bar_done);
     }
   } else {
-    // ===== H warpgroups: both work on every tile; warpgroup g takes columns 32g..32g+31 =====
+    // ===== H warpgroups: warpgroup g takes tiles t = g, g+2, ... (S/H buffer g) =====
     const int wg = (warp - 2) >> 2;
     const int lrow = 32 * (warp & 3) + lane;
     const int gi = row0 + lrow;
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    if (wg == 0) {
+      load_rows_to_tmem(z, gi, a.n_total, tmem + lane_addr + TM_A);
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&bar_a);
+    }
     const int gic = min(gi, a.n_pad - 1);
     const int lab_r = a.lab_pad[gic];
     const float A_r = a.colA[gic], B_r = a.colB[gic];
     const float nrm_r = UNI ? a.nrm_pad[gic] : 0.f;
     const float cu = UNI ? a.scalars[0] : 0.f;
-    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
-    for (int t = 0; t < ntiles; ++t) {
-      const int buf = t & 1, buse = t >> 1, slot = t % RING;
+    const uint32_t sbuf = tmem + lane_addr + TM_S + wg * BN;
+    for (int t = wg; t < ntiles; t += 2) {
+      const int buse = t >> 1, slot = t % RING;
       const int col0 = (ct_begin + t) * BN;
-      ColVecs cv;
-      cv.lab = lab_ring[slot] + 32 * wg; cv.A = colA_ring[slot] + 32 * wg; cv.B = colB_ring[slot] + 32 * wg;
-      cv.nrm = nrm_ring[UNI ? slot : 0] + 32 * wg;
       ptx::mbar_wait(&bar_col[slot], (t / RING) & 1);
-      ptx::mbar_wait(&bar_sfull[buf], buse & 1);
+      ptx::mbar_wait(&bar_sfull[wg], buse & 1);
       ptx::tc_fence_after_sync();
-      uint32_t r[32];
-      ptx::tmem_ld32(tmem + lane_addr + TM_S + buf * BN + 32 * wg, r);
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld32(sbuf, r0);
+      ptx::tmem_ld32(sbuf + 32, r1);
       ptx::tmem_ld_wait();
-      ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&bar_sempty[buf]);
-      uint32_t hw[16];
+      uint32_t hw[32];
+      uint32_t (&h0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[0]);
+      uint32_t (&h1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[16]);
+      ColVecs cv0, cv1;
+      cv0.lab = lab_ring[slot]; cv0.A = colA_ring[slot]; cv0.B = colB_ring[slot]; cv0.nrm = nrm_ring[UNI ? slot : 0];
+      cv1.lab = cv0.lab + 32; cv1.A = cv0.A + 32; cv1.B = cv0.B + 32; cv1.nrm = cv0.nrm + 32;
       const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
-      if (masked) bwd_chunk<SIM, UNI, true>(r, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, cv, a);
-      else bwd_chunk<SIM, UNI, false>(r, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, cv, a);
-      ptx::mbar_wait(&bar_hempty[buf], (buse & 1) ^ 1);
-      const uint32_t hbase = ptx::smem_u32(sH + buf * H_BYTES) + lrow * 128;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int chunk = 4 * wg + q;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hbase + ((chunk ^ (lrow & 7)) << 4)),
-                     "r"(hw[4 * q]), "r"(hw[4 * q + 1]), "r"(hw[4 * q + 2]), "r"(hw[4 * q + 3])
-                     : "memory");
+      if (masked) {
+        bwd_chunk<SIM, UNI, true>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, a);
+        bwd_chunk<SIM, UNI, true>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, a);
+      } else {
+        bwd_chunk<SIM, UNI, false>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, a);
+        bwd_chunk<SIM, UNI, false>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, a);
       }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&bar_hfull[buf]);
+      ptx::tmem_st32(sbuf, hw);            // H(t): 64 bf16 = 32 packed columns over S(t)
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&bar_hfull[wg]);
     }
     // ---- epilogue: dZ rows out of TMEM; warpgroup g writes columns 128g..128g+127 ----
     ptx::mbar_wait(&bar_done, 0);
@@ -576,6 +586,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<512>(tmem);
 }
+
 
 // sum the column splits, add the uniformity diagonal term, scale by grad_out, convert
 template <typename TO>
@@ -643,9 +654,10 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.n_pad = (int)align_up((size_t)p->n_total, 128);
   pl.rows_pad = (int)align_up((size_t)p->n_rows, 128);
   pl.row_blocks = pl.rows_pad / 128;
+  pl.fwd_row_blocks = (pl.row_blocks + 1) / 2;   // forward CTAs own two 128-row blocks
   pl.fwd_col_tiles = pl.n_pad / 128;
   pl.bwd_col_tiles = (p->n_total + 63) / 64;
-  pl.fwd_splits = choose_splits(pl.row_blocks, pl.fwd_col_tiles, num_sms());
+  pl.fwd_splits = choose_splits(pl.fwd_row_blocks, pl.fwd_col_tiles, num_sms());
   pl.bwd_splits = choose_splits(pl.row_blocks, pl.bwd_col_tiles / 2, num_sms());
   pl.merge_blocks = pl.rows_pad / 128;
   size_t off = 256;
@@ -675,10 +687,11 @@ bool tc_supported(const supcon_problem_t* p) {
 }
 
 template <int SIM, bool UNI>
-static cudaError_t launch_fwd(const CUtensorMap& tm, const TcFwdArgs& a, int ctas, size_t smem, cudaStream_t st) {
+static cudaError_t launch_fwd(const CUtensorMap& tm, const __nv_bfloat16* z, const TcFwdArgs& a, int ctas, size_t smem,
+                              cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<SIM, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_fwd_kernel<SIM, UNI><<<ctas, NTHREADS, smem, st>>>(tm, a);
+  tc_fwd_kernel<SIM, UNI><<<ctas, NTHREADS, smem, st>>>(tm, z, a);
   return cudaGetLastError();
 }
 
@@ -711,12 +724,13 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
   a.inv_tau = 1.0f / p->tau;
   a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
   const size_t smem = 3 * (size_t)NBOX * 128 * 128 + 1024;
-  const int ctas = pl.row_blocks * pl.fwd_splits;
+  const int ctas = pl.fwd_row_blocks * pl.fwd_splits;
   const bool geo = p->similarity == SUPCON_GEODESIC;
-  if (geo && uni) e = launch_fwd<SUPCON_GEODESIC, true>(tm, a, ctas, smem, stream);
-  else if (geo) e = launch_fwd<SUPCON_GEODESIC, false>(tm, a, ctas, smem, stream);
-  else if (uni) e = launch_fwd<SUPCON_COSINE, true>(tm, a, ctas, smem, stream);
-  else e = launch_fwd<SUPCON_COSINE, false>(tm, a, ctas, smem, stream);
+  const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
+  if (geo && uni) e = launch_fwd<SUPCON_GEODESIC, true>(tm, zb, a, ctas, smem, stream);
+  else if (geo) e = launch_fwd<SUPCON_GEODESIC, false>(tm, zb, a, ctas, smem, stream);
+  else if (uni) e = launch_fwd<SUPCON_COSINE, true>(tm, zb, a, ctas, smem, stream);
+  else e = launch_fwd<SUPCON_COSINE, false>(tm, zb, a, ctas, smem, stream);
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
   FinishArgs f{reinterpret_cast<double*>(ws + pl.off_block_partials), reinterpret_cast<unsigned*>(ws), partials,
                loss_out, p->n_total, p->tau, p->alpha, p->lambda_uni, p->uni_t};
@@ -727,11 +741,11 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
 }
 
 template <int SIM, bool UNI>
-static cudaError_t launch_bwd(const CUtensorMap& tmI, const CUtensorMap& tmJ, const TcBwdArgs& a, int ctas, size_t smem,
+static cudaError_t launch_bwd(const CUtensorMap& tmJ, const __nv_bfloat16* z, const TcBwdArgs& a, int ctas, size_t smem,
                               cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<SIM, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_bwd_kernel<SIM, UNI><<<ctas, NTHREADS, smem, st>>>(tmI, tmJ, a);
+  tc_bwd_kernel<SIM, UNI><<<ctas, NTHREADS, smem, st>>>(tmJ, z, a);
   return cudaGetLastError();
 }
 
@@ -740,9 +754,8 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
                 cudaStream_t stream, const char** err) {
   const TcPlan pl = tc_plan(p);
   char* ws = reinterpret_cast<char*>(workspace);
-  CUtensorMap tmI, tmJ;
-  if (make_bf16_rowmajor_tmap(&tmI, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 128) != 0 ||
-      make_bf16_rowmajor_tmap(&tmJ, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 64) != 0) {
+  CUtensorMap tmJ;
+  if (make_bf16_rowmajor_tmap(&tmJ, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 64) != 0) {
     *err = "cuTensorMapEncodeTiled failed (z must be 16-byte aligned)";
     return SUPCON_E_INVALID;
   }
@@ -776,13 +789,14 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   a.rows_pad = pl.rows_pad; a.splits = pl.bwd_splits; a.col_tiles = pl.bwd_col_tiles;
   a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
   a.scalars = pa.scalars;
-  const size_t smem = (size_t)NBOX * 128 * 128 + 3 * (size_t)NBOX * 64 * 128 + 2 * 128 * 64 * 2 + 1024;
+  const size_t smem = 4 * (size_t)NBOX * 64 * 128 + 1024;
   const int ctas = pl.row_blocks * pl.bwd_splits;
   const bool geo = p->similarity == SUPCON_GEODESIC;
-  if (geo && uni) e = launch_bwd<SUPCON_GEODESIC, true>(tmI, tmJ, a, ctas, smem, stream);
-  else if (geo) e = launch_bwd<SUPCON_GEODESIC, false>(tmI, tmJ, a, ctas, smem, stream);
-  else if (uni) e = launch_bwd<SUPCON_COSINE, true>(tmI, tmJ, a, ctas, smem, stream);
-  else e = launch_bwd<SUPCON_COSINE, false>(tmI, tmJ, a, ctas, smem, stream);
+  const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
+  if (geo && uni) e = launch_bwd<SUPCON_GEODESIC, true>(tmJ, zb, a, ctas, smem, stream);
+  else if (geo) e = launch_bwd<SUPCON_GEODESIC, false>(tmJ, zb, a, ctas, smem, stream);
+  else if (uni) e = launch_bwd<SUPCON_COSINE, true>(tmJ, zb, a, ctas, smem, stream);
+  else e = launch_bwd<SUPCON_COSINE, false>(tmJ, zb, a, ctas, smem, stream);
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
   const int64_t n4 = (int64_t)p->n_rows * (TD / 4);
   const int blocks = (int)((n4 + 255) / 256);
