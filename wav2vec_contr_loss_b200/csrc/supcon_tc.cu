@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
       const int st = t % STAGES, use = t / STAGES, slot = t % RING;
       const int col0 = (ct_begin + t) * BN;
       ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&bar_full[st], TILE_BYTES);
         for (int b = 0; b < NBOX; ++b)
           ptx::tma_load_2d(sZJ + st * TILE_BYTES + b * BOX_BYTES, &tmap, &bar_full[st], 64 * b, col0);
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::idesc_bf16(128, BN, false, false);
       ptx::mbar_wait(&bar_a, 0);
       for (int t = 0; t < ntiles; ++t) {
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       const int col0 = (ct_begin + t) * BN;
       // stage/slot st was last used by tile t-4; its release (dZ(t-4) complete) implies H(t-4) was formed
       ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&bar_full[st], TILEJ_BYTES);
         for (int b = 0; b < NBOX; ++b)
           ptx::tma_load_2d(sZJ + st * TILEJ_BYTES + b * BOXJ_BYTES, &tmapJ, &bar_full[st], 64 * b, col0);
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer: iteration t issues S(t) and then dZ(t-1) =====
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       constexpr uint32_t idesc_s = ptx::idesc_bf16(128, BN, false, false);
       constexpr uint32_t idesc_dz = ptx::idesc_bf16(128, TD, false, true);
       ptx::mbar_wait(&bar_a, 0);
