@@ -19,6 +19,8 @@
 // alloc), warps 2..9 = eight softmax/epilogue warps (two warpgroups).
 // Preconditions of this path (checked by the dispatcher): bf16 z, d == 256,
 // tau >= 0.025, rows L2-normalised (what the callers pass, stage1_utils.py:123).
+#include <stdlib.h>
+
 #include "supcon_common.cuh"
 #include "supcon_internal.h"
 #include "tc_ptx.cuh"
@@ -622,15 +624,29 @@ __global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const _
   }
 }
 
-int choose_splits(int row_blocks, int col_tiles, int num_sms) {
-  // enough CTAs for ~7 waves so the tail is small, but at least 8 column tiles per CTA
-  int target = 7 * num_sms;
-  int s = (target + row_blocks - 1) / row_blocks;
-  int max_s = col_tiles / 8 > 0 ? col_tiles / 8 : 1;
-  if (s > max_s) s = max_s;
-  if (s < 1) s = 1;
-  if (s > 64) s = 64;
-  return s;
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// Column splits per row block.  All CTAs are equal-sized, so the launch runs in
+// ceil(ctas / SMs) waves; pick the split count that maximises
+//   (wave balance) x (useful tiles / (useful tiles + per-CTA prologue/epilogue cost in tiles)).
+int choose_splits(int row_blocks, int col_tiles, int num_sms, const char* env_override, int overhead_tiles) {
+  int forced = env_int(env_override, 0);
+  if (forced > 0) return forced > col_tiles ? col_tiles : forced;
+  int best = 1;
+  double best_eff = 0.0;
+  const int max_s = col_tiles < 64 ? col_tiles : 64;
+  for (int sp = 1; sp <= max_s; ++sp) {
+    const double ctas = (double)row_blocks * sp;
+    const double waves = ceil(ctas / num_sms);
+    const double balance = ctas / (waves * num_sms);
+    const double tiles = (double)col_tiles / sp;
+    const double eff = balance * tiles / (tiles + overhead_tiles);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
+  }
+  return best;
 }
 
 int g_num_sms = 0;
@@ -657,8 +673,8 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.fwd_row_blocks = (pl.row_blocks + 1) / 2;   // forward CTAs own two 128-row blocks
   pl.fwd_col_tiles = pl.n_pad / 128;
   pl.bwd_col_tiles = (p->n_total + 63) / 64;
-  pl.fwd_splits = choose_splits(pl.fwd_row_blocks, pl.fwd_col_tiles, num_sms());
-  pl.bwd_splits = choose_splits(pl.row_blocks, pl.bwd_col_tiles / 2, num_sms());
+  pl.fwd_splits = choose_splits(pl.fwd_row_blocks, pl.fwd_col_tiles, num_sms(), "SUPCON_TC_FWD_SPLITS", env_int("SUPCON_TC_FWD_OVH", 5));
+  pl.bwd_splits = choose_splits(pl.row_blocks, pl.bwd_col_tiles, num_sms(), "SUPCON_TC_BWD_SPLITS", env_int("SUPCON_TC_BWD_OVH", 12));
   pl.merge_blocks = pl.rows_pad / 128;
   size_t off = 256;
   pl.off_block_partials = off; off += align_up((size_t)pl.merge_blocks * SUPCON_N_PARTIALS * sizeof(double), 256);
