@@ -2,7 +2,7 @@
 """Benchmark of the SupCon hot path (BASELINE.json metric: fwd+bwd sim-pairs/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--n 65536] [--d 256] [--dtype bf16|f32] [--similarity cosine]
+                    [--batch-n 65536] [--d 256] [--dtype bf16|f32] [--similarity cosine]
 
 One "step" = one forward + backward of the loss over one batch of synthetic
 unit-norm embeddings (value = N^2 / t).  Default workload = BASELINE.json
@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--batch-n", dest="n", type=int, default=65536)
     ap.add_argument("--d", type=int, default=256)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--similarity", default="cosine")
@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-sample-n", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -166,7 +167,8 @@ def workload_config(args, extra=None):
            "N": args.n, "d": args.d, "similarity": args.similarity, "tau": args.tau,
            "lambda_uni": args.lambda_uni, "topk": args.topk, "alpha": args.alpha,
            "parallelism": f"rows sharded over {args.gpus} rank(s)",
-           "l2_flush": "256 MiB memset between timed iterations, outside the per-step CUDA events"}
+           "l2_flush": "256 MiB memset between timed iterations, outside the per-step CUDA events",
+           "launch": "eager" if args.no_graph else "one CUDA-graph replay per step"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -235,8 +237,38 @@ def main():
         dz = Fn.backward_rows(z_all, y_all, stats_all, partials, None, prob, out_dtype=tdtype)
         if timing:
             timing[3].record()
-        launches["count"] += 2 + (1 if world > 1 else 0)
+        # kernels of libsupcon_b200.so per step on the tensor path: prep_fwd, tc_fwd, merge, prep_bwd, tc_bwd,
+        # reduce (+ finalize when the loss comes from all-reduced partials)
+        launches["count"] += 6 + (1 if world > 1 else 0)
         return loss, dz
+
+    class Stepper:
+        """One step = one CUDA-graph replay (captured once, NCCL collectives included) unless --no-graph."""
+
+        def __init__(self, fn):
+            self.fn, self.graph, self.out = fn, None, None
+            if not args.no_graph:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    fn()
+                    torch.cuda.synchronize()
+                    if world > 1:
+                        dist.barrier()
+                    self.graph = torch.cuda.CUDAGraph()
+                    n0 = launches["count"]
+                    with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
+                        self.out = fn()
+                    self.per_step = launches["count"] - n0
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+
+        def __call__(self):
+            if self.graph is None:
+                return self.fn()
+            self.graph.replay()
+            launches["count"] += self.per_step
+            return self.out
 
     def barrier():
         if world > 1:
@@ -245,6 +277,20 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step(z_local, y_local)
+    barrier()
+    resident = Stepper(lambda: step(z_local, y_local))
+
+    def e2e_step():
+        zl = zl_host.to(dev, non_blocking=True)
+        yl = yl_host.to(dev, non_blocking=True)
+        loss, dz = step(zl, yl)
+        loss_host.copy_(loss.float(), non_blocking=True)
+        return loss, dz
+
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    e2e = Stepper(e2e_step)
+    for _ in range(2):
+        resident(); e2e()
     barrier()
 
     # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed between steps ----
@@ -257,7 +303,7 @@ def main():
     for s, e in ev:
         flush.zero_()
         s.record()
-        loss, dz = step(z_local, y_local)
+        loss, dz = resident()
         e.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -270,16 +316,12 @@ def main():
     ms_per_step = float(tt)
 
     # ---- end-to-end: pinned host inputs -> H2D -> fwd+bwd -> loss D2H, every step ----
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for s, e in ev2:
         flush.zero_()
         s.record()
-        zl = zl_host.to(dev, non_blocking=True)
-        yl = yl_host.to(dev, non_blocking=True)
-        loss, dz = step(zl, yl)
-        loss_host.copy_(loss.float(), non_blocking=True)
+        e2e()
         e.record()
     barrier()
     t2 = torch.tensor([sum(s.elapsed_time(e) for s, e in ev2) / len(ev2)], device=dev, dtype=torch.float64)
@@ -338,7 +380,13 @@ def main():
                                               f"of loss.py, median of 3, {tc:.2f} s per fwd+bwd"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing the process group down while captured NCCL graphs are alive can block; every rank has
+        # finished its work, so synchronise and leave without running the destructors.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
