@@ -18,13 +18,14 @@ TOL_F32 = 1e-5      # north_star: fp32 / tf32-off path
 TOL_BF16 = 2e-3     # north_star: bf16 input, fp32 accumulate
 
 
+@pytest.mark.parametrize("flags", [0, 4])     # 0: small batches take the single-launch cluster kernel; 4: tiled FFMA kernels
 @pytest.mark.parametrize("name", golden_names())
-def test_golden_fixtures_fp32(cuda_device, name):
+def test_golden_fixtures_fp32(cuda_device, name, flags):
     meta, g = load_golden(name)
     z, y = torch.from_numpy(g["z"]), torch.from_numpy(g["labels"])
     kw = dict(tau=meta["tau"], similarity=meta["similarity"], lam=meta["lambda_uni"], t=meta["uni_t"],
               topk=meta["topk"], alpha=meta["alpha"])
-    loss, dz = G.kernel_loss_and_grad(z, y, **kw)
+    loss, dz = G.kernel_loss_and_grad(z, y, flags=flags, **kw)
     assert loss == pytest.approx(float(g["loss64"]), rel=TOL_F32, abs=1e-6)
     assert loss == pytest.approx(float(g["loss32"]), rel=TOL_F32, abs=1e-6)
     if meta["n"] < 2:
@@ -93,17 +94,22 @@ def _exact_arith_inputs(n, d, seed):
 @pytest.mark.parametrize("n,d,k", [(96, 8, 7), (300, 12, 15), (1024, 16, 32)])
 def test_hard_negative_index_sets_exact(cuda_device, n, d, k):
     z, y = _exact_arith_inputs(n, d, seed=n)
-    out = G.kernel_stats(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0)
+    out = G.kernel_stats(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0, flags=4)
     ref = G.oracle_for(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0, want_topk_idx=True, want_grad=False)
     got = out["idx"].cpu().tolist()
     for i in range(n):
         mine = [j for j in got[i] if j >= 0]
         assert mine == sorted(ref["stats"]["topk_idx"][i]), f"row {i}"
     # and the gradient that depends on those sets
-    loss, dz = G.kernel_loss_and_grad(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0)
     full = G.oracle_for(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0)
-    assert loss == pytest.approx(full["loss"], rel=TOL_F32)
-    assert G.rel_err(dz, full["dz"]) < TOL_F32
+    for flags in (0, 4):     # the cluster kernel (n <= 160) must pick the same sets: same gradient
+        loss, dz = G.kernel_loss_and_grad(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0, flags=flags)
+        assert loss == pytest.approx(full["loss"], rel=TOL_F32)
+        assert G.rel_err(dz, full["dz"]) < TOL_F32
+    if n <= 160:             # threshold (value, index) written by the cluster kernel == tiled kernel
+        small = G.kernel_stats(z, y, tau=0.5, similarity="cosine", topk=k, alpha=1.0, flags=0)
+        assert torch.equal(small["stats"].view(torch.int32)[:, 5].cpu(), out["stats"].view(torch.int32)[:, 5].cpu())
+        assert torch.equal(small["stats"][:, 4].cpu(), out["stats"][:, 4].cpu())
 
 
 def test_appendix_b_tie_case(cuda_device):
@@ -111,8 +117,11 @@ def test_appendix_b_tie_case(cuda_device):
     y = torch.tensor([1, 1, 0, 0, 0, 0])
     loss, dz = G.kernel_loss_and_grad(z, y, tau=0.5, similarity="cosine", topk=2, alpha=1.0)
     assert loss == pytest.approx(1.0041676759719849, rel=TOL_F32)
-    out = G.kernel_stats(z, y, tau=0.5, similarity="cosine", topk=2, alpha=1.0)
-    assert out["idx"][0].tolist() == [2, 5] and out["idx"][1].tolist() == [2, 5]
+    for flags in (0, 4):
+        out = G.kernel_stats(z, y, tau=0.5, similarity="cosine", topk=2, alpha=1.0, flags=flags)
+        assert out["idx"][0].tolist() == [2, 5] and out["idx"][1].tolist() == [2, 5]
+        loss, dz = G.kernel_loss_and_grad(z, y, tau=0.5, similarity="cosine", topk=2, alpha=1.0, flags=flags)
+        assert loss == pytest.approx(1.0041676759719849, rel=TOL_F32)
 
 
 def test_analytic_known_answers(cuda_device):

@@ -109,9 +109,32 @@ def time_case(n, d, dtype, sim, tau, lam, k, alpha, flags, iters=20):
         graph_us = 1e3 * e0.elapsed_time(e1) / reps
     except Exception as e:  # noqa: BLE001
         graph_us = f"graph failed: {e}"
+    fused_us = None
+    if n <= Fn.SMALL_BATCH_MAX:
+        # the single-launch path (supcon_loss_and_grad), CUDA-graph replay = device time of fwd+bwd
+        try:
+            g2 = torch.cuda.CUDAGraph()
+            s2 = torch.cuda.Stream()
+            s2.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s2):
+                Fn.loss_and_grad(z, yl, prob)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g2, stream=s2):
+                    Fn.loss_and_grad(z, yl, prob)
+            torch.cuda.synchronize()
+            for _ in range(5):
+                g2.replay()
+            e0.record()
+            for _ in range(200):
+                g2.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            fused_us = 1e3 * e0.elapsed_time(e1) / 200
+        except Exception as e:  # noqa: BLE001
+            fused_us = f"failed: {e}"
     flops = (6 + (2 if lam > 0 else 0)) * n * n * d
     return dict(n=n, d=d, dtype=str(dtype)[6:], sim=sim, lam=lam, k=k, alpha=alpha, flags=flags, fwd_ms=fw,
-                bwd_ms=bw, graph_us=graph_us, pairs_per_s=n * n / ((fw + bw) * 1e-3),
+                bwd_ms=bw, graph_us=graph_us, fused_graph_us=fused_us, pairs_per_s=n * n / ((fw + bw) * 1e-3),
                 tflops=flops / ((fw + bw) * 1e-3) / 1e12)
 
 
@@ -151,6 +174,7 @@ def main():
     if args.perf:
         for (n, dtype, sim, lam, k, alpha) in [
                 (64, f32, "cosine", 0.0, 15, 0.0), (64, f32, "geodesic", 0.05, 15, 0.0),
+                (64, f32, "cosine", 0.0, 15, 0.5), (128, f32, "cosine", 0.0, 15, 0.0), (160, f32, "geodesic", 0.05, 15, 0.5),
                 (256, f32, "cosine", 0.0, 15, 0.0), (1024, f32, "cosine", 0.0, 15, 0.0),
                 (1024, f32, "cosine", 0.0, 15, 0.5), (1024, bf16, "cosine", 0.0, 15, 0.5),
                 (4096, f32, "cosine", 0.0, 15, 0.0), (16384, bf16, "cosine", 0.0, 15, 0.0)]:

@@ -75,6 +75,21 @@ bool vec_ok(const void* z, const supcon_problem_t* p) {
   return (p->d % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) % al) == 0);
 }
 
+bool use_small(const supcon_problem_t* p, const void* z) {
+  if (p->flags & (SUPCON_FLAG_NO_SMALL | SUPCON_FLAG_FORCE_TENSOR)) return false;
+  return small_supported(p, z);
+}
+
+SmallArgs make_small(const supcon_problem_t* p, const void* z, const int32_t* labels) {
+  SmallArgs s;
+  memset(&s, 0, sizeof(s));
+  s.z = z; s.labels = labels;
+  s.n = p->n_total; s.d = p->d; s.z_dtype = p->z_dtype; s.dz_dtype = SUPCON_F32; s.similarity = p->similarity;
+  s.topk = p->topk < 0 ? 0 : p->topk; s.mine = needs_mining(p) ? 1 : 0;
+  s.tau = p->tau; s.alpha = p->alpha; s.lambda_uni = p->lambda_uni; s.uni_t = p->uni_t;
+  return s;
+}
+
 FfmaArgs make_ffma(const supcon_problem_t* p, const void* z, const int32_t* labels, void* ws) {
   FfmaArgs a;
   memset(&a, 0, sizeof(a));
@@ -163,6 +178,13 @@ int supcon_forward_rows(const supcon_problem_t* p, const void* z_all, const int3
   if (loss_out && (p->row_offset != 0 || p->n_rows != p->n_total))
     return fail(SUPCON_E_INVALID, "loss_out needs a rank that owns every row; use supcon_finalize");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use_small(p, z_all)) {   // whole batch on this rank, small N: one launch, statistics + loss only
+    SmallArgs s = make_small(p, z_all, labels_all);
+    s.row_stats = row_stats; s.partials = partials; s.loss_out = loss_out;
+    cudaError_t es = small_launch(s, st);
+    if (es != cudaSuccess) return cuda_fail(es, "small_launch");
+    return 0;
+  }
   if (use_tc(p, false)) {
     const char* err = "";
     int rc = tc_forward(p, z_all, labels_all, row_stats, partials, loss_out, workspace, st, &err);
@@ -223,6 +245,16 @@ int supcon_loss_and_grad(const supcon_problem_t* p, const void* z, const int32_t
   if (p->row_offset != 0 || p->n_rows != p->n_total)
     return fail(SUPCON_E_INVALID, "supcon_loss_and_grad needs the whole batch on one rank");
   if (!loss_out) return fail(SUPCON_E_INVALID, "loss_out is NULL");
+  if (!z || !labels) return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_loss_and_grad");
+  if (dz_out && dz_dtype != SUPCON_F32 && dz_dtype != SUPCON_BF16)
+    return fail(SUPCON_E_INVALID, "unknown dz_dtype %d", dz_dtype);
+  if (use_small(p, z)) {   // forward AND backward in a single cluster launch
+    SmallArgs s = make_small(p, z, labels);
+    s.row_stats = row_stats; s.partials = partials; s.loss_out = loss_out; s.dz_out = dz_out; s.dz_dtype = dz_dtype;
+    cudaError_t es = small_launch(s, reinterpret_cast<cudaStream_t>(stream));
+    if (es != cudaSuccess) return cuda_fail(es, "small_launch");
+    return 0;
+  }
   int rc = supcon_forward_rows(p, z, labels, row_stats, partials, loss_out, workspace, workspace_bytes, stream);
   if (rc) return rc;
   if (dz_out)

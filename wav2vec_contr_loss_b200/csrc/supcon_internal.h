@@ -70,6 +70,21 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
                 const double* partials_global, const float* grad_out, void* dz_out, int dz_dtype, void* workspace,
                 cudaStream_t stream, const char** err);
 
+// ---- single-launch small-batch path (supcon_small.cu) ----
+struct SmallArgs {
+  const void* z;
+  const int32_t* labels;
+  float* row_stats;       // optional [n][STRIDE]
+  double* partials;       // optional [8]
+  float* loss_out;        // optional
+  void* dz_out;           // optional [n][d]
+  const float* grad_out;  // optional device scalar
+  int n, d, z_dtype, dz_dtype, similarity, topk, mine;
+  float tau, alpha, lambda_uni, uni_t;
+};
+bool small_supported(const supcon_problem_t* p, const void* z);
+cudaError_t small_launch(const SmallArgs& a, cudaStream_t stream);
+
 // tcgen05 building-block diagnostic (supcon_tc_debug.cu)
 int tc_debug_tile(const void* z_bf16, int n, int d, int row_i, int row_j, float* s_out, float* o_out,
                   cudaStream_t stream, const char** err);

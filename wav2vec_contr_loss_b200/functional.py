@@ -100,6 +100,29 @@ def forward_rows(z_all: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Prob
     return stats, partials, loss
 
 
+def loss_and_grad(z: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Problem, want_grad: bool = True,
+                  out_dtype=torch.float32):
+    """Whole batch on one GPU through supcon_loss_and_grad (one launch for small batches).
+    Returns (loss, dz or None, row_stats, partials); dz is d loss / d z for grad_out = 1."""
+    _require_cuda(z, "z")
+    lib = _cabi.load()
+    dev = z.device
+    with torch.cuda.device(dev):
+        stats = torch.empty((prob.n_rows, _cabi.STATS_STRIDE), dtype=torch.float32, device=dev)
+        partials = torch.empty(_cabi.N_PARTIALS, dtype=torch.float64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dz = torch.empty((prob.n_rows, prob.d), dtype=out_dtype, device=dev) if want_grad else None
+        ws = workspace_for(prob, dev)
+        _cabi.check(lib.supcon_loss_and_grad(ctypes.byref(prob), _p(z), _p(labels_i32), _p(loss), _p(dz),
+                                             _dtype_id(dz) if dz is not None else 0, _p(stats), _p(partials),
+                                             _p(ws), ws.numel(), _stream(dev)),
+                    "supcon_loss_and_grad")
+    return loss, dz, stats, partials
+
+
+SMALL_BATCH_MAX = 160   # supcon_small.cu: N <= 8 CTAs x 20 rows
+
+
 def finalize(prob: _cabi.Problem, partials_global: torch.Tensor) -> torch.Tensor:
     lib = _cabi.load()
     dev = partials_global.device
@@ -156,6 +179,14 @@ class SupConFunction(torch.autograd.Function):
         n, d = zc.shape
         prob = make_problem(n, d, _dtype_id(zc), tau=tau, similarity=sim_id, lambda_uni=lambda_uni,
                             uni_t=uni_t, topk=topk, alpha=alpha, flags=flags)
+        ctx.fused = False
+        if ctx.needs_input_grad[0] and n <= SMALL_BATCH_MAX and not (flags & (_cabi.FLAG_NO_SMALL | _cabi.FLAG_FORCE_TENSOR)):
+            # small batch: forward and backward in ONE launch; backward() only scales by grad_out
+            loss, dz, _, _ = loss_and_grad(zc, labels_i32, prob, want_grad=True, out_dtype=zc.dtype)
+            ctx.save_for_backward(dz)
+            ctx.fused = True
+            ctx.in_dtype = z.dtype
+            return _loss_dtype(loss, z.dtype)
         stats, partials, loss = forward_rows(zc, labels_i32, prob, want_loss=True)
         if ctx.needs_input_grad[0]:
             ctx.save_for_backward(zc, labels_i32, stats, partials)
@@ -165,6 +196,9 @@ class SupConFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.fused:
+            (dz,) = ctx.saved_tensors
+            return (dz * grad_out.to(dz.dtype)).to(ctx.in_dtype), None, None, None, None, None, None, None, None
         zc, labels_i32, stats, partials = ctx.saved_tensors
         out_dtype = zc.dtype
         dz = backward_rows(zc, labels_i32, stats, partials, grad_out, ctx.prob, out_dtype=out_dtype)
