@@ -184,6 +184,7 @@ def main():
     from wav2vec_contr_loss_b200 import build as _build
     _build.build()
     from wav2vec_contr_loss_b200 import functional as Fn
+    from wav2vec_contr_loss_b200.distributed import exchange_stats, gather_inputs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -213,10 +214,7 @@ def main():
     def step(z_loc, y_loc, timing=None):
         """fwd + bwd through the C-ABI wrappers; returns (loss, dz_local)."""
         if world > 1:
-            z_all = torch.empty((n, d), dtype=tdtype, device=dev)
-            y_all = torch.empty(n, dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(z_all, z_loc)
-            dist.all_gather_into_tensor(y_all, y_loc)
+            z_all, y_all = gather_inputs(z_loc, y_loc)
         else:
             z_all, y_all = z_loc, y_loc
         prob = Fn.make_problem(n, d, Fn._dtype_id(z_all), row_offset=rank * n_local, n_rows=n_local, **kw)
@@ -226,10 +224,8 @@ def main():
         if timing:
             timing[1].record()
         if world > 1:
-            dist.all_reduce(partials)
+            stats_all = exchange_stats(partials, stats)
             loss = Fn.finalize(prob, partials)
-            stats_all = torch.empty((n, 8), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(stats_all, stats)
         else:
             stats_all = stats
         if timing:

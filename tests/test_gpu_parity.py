@@ -343,3 +343,37 @@ def test_large_batch_properties_bf16(cuda_device):
                             out_dtype=torch.float32).cpu()
     assert float(out_p["loss"]) == pytest.approx(float(out["loss"]), rel=1e-5)
     assert G.rel_err(dz_p, dz[perm]) < TOL_BF16
+
+
+TC_MINING_CASES = [
+    # n, kind, classes, sim, tau, lam, alpha, K
+    (1024, "iso", 2, "cosine", 0.07, 0.0, 0.5, 15),        # BASELINE config 3 in bf16
+    (1024, "iso", 2, "cosine", 0.07, 0.0, 0.0125, 15),
+    (1000, "iso", 3, "cosine", 0.07, 0.0, 1.0, 32),
+    (640, "clustered", 2, "geodesic", 0.1, 0.05, 0.37, 5),
+    (2048, "ties", 2, "cosine", 0.07, 0.0, 1.0, 15),       # exact duplicates: ties at the K-th boundary
+]
+
+
+@pytest.mark.parametrize("n,kind,classes,sim,tau,lam,alpha,k", TC_MINING_CASES)
+def test_tensor_core_path_mining(cuda_device, n, kind, classes, sim, tau, lam, alpha, k):
+    """Hard-negative mining fused into the tcgen05 kernels: the selected sets (threshold index per row)
+    must equal the stable-sort oracle's, loss/dz within the bf16 tolerance."""
+    from wav2vec_contr_loss_b200 import functional as Fn
+    x, y = O.make_inputs(n, 256, kind, classes=classes)
+    zb = F.normalize(x, dim=1).to(torch.bfloat16)
+    kw = dict(tau=tau, similarity=sim, lam=lam, t=2.0, topk=k, alpha=alpha)
+    ref = G.oracle_for(zb.float(), y, **kw)
+    prob_kw = dict(kw)
+    z = Fn.canonical_z(zb.to(cuda_device))
+    yy = Fn.canonical_labels(y.to(cuda_device), n)
+    prob = Fn.make_problem(n, 256, 1, tau=tau, similarity=Fn.similarity_id(sim), lambda_uni=lam, uni_t=2.0, topk=k,
+                           alpha=alpha, flags=2)
+    stats, partials, loss = Fn.forward_rows(z, yy, prob, want_loss=True)
+    assert float(loss) == pytest.approx(ref["loss"], rel=TOL_BF16)
+    st = stats.cpu()
+    if sim == "cosine":      # exact products of bf16 inputs: the ranking is identical to the fp64 oracle's
+        assert torch.equal(st.view(torch.int32)[:, 5].long(), ref["stats"]["thr_idx"])
+    assert float((st[:, 1].double() - ref["stats"]["lse_m"]).abs().max()) < 1e-4
+    dz = Fn.backward_rows(z, yy, stats, partials, None, prob, out_dtype=torch.float32)
+    assert G.rel_err(dz.cpu(), ref["dz"]) < TOL_BF16

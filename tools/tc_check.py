@@ -24,6 +24,10 @@ cases = [
     (512, "iso", 2, "geodesic", 0.07, 0.0, 0.0, 15),
     (777, "iso", 5, "geodesic", 0.1, 0.2, 0.0, 15),
     (2048, "iso", 2, "cosine", 0.07, 0.0, 0.0, 0),
+    (1024, "iso", 2, "cosine", 0.07, 0.0, 0.5, 15),      # hard-negative mining on the tensor path
+    (1000, "iso", 3, "cosine", 0.07, 0.0, 1.0, 32),
+    (640, "clustered", 2, "geodesic", 0.1, 0.05, 0.37, 5),
+    (2048, "ties", 2, "cosine", 0.07, 0.0, 1.0, 15),
 ]
 if args.big:
     cases += [(4096, "iso", 2, "cosine", 0.07, 0.0, 0.0, 15), (8192, "iso", 2, "cosine", 0.07, 0.05, 0.0, 15)]
@@ -43,6 +47,10 @@ for (n, kind, classes, sim, tau, lam, alpha, k) in cases:
             rec["pos_mean_err"] = float((st[:, 7].double() - ref["stats"]["pos_mean"]).abs().max())
             rec["wsum_rel"] = float((st[:, 6].double() - ref["stats"]["wsum"]).abs().max() / max(float(ref["stats"]["wsum"].abs().max()), 1e-30))
             rec["npos_eq"] = bool((st.view(torch.int32)[:, 2].long() == ref["stats"]["npos"]).all())
+            if alpha != 0:
+                rec["lse_m_err"] = float((st[:, 1].double() - ref["stats"]["lse_m"]).abs().max())
+                rec["thr_idx_eq"] = float((st.view(torch.int32)[:, 5].long() == ref["stats"]["thr_idx"]).float().mean())
+                rec["thr_val_err"] = float((st[:, 4].double() - ref["stats"]["thr_val"]).abs().max())
             rec["loss"] = float(out["loss"]); rec["loss_ref"] = ref["loss"]
             rec["loss_rel"] = abs(rec["loss"] - ref["loss"]) / abs(ref["loss"])
             # backward through the C-ABI with fp32 dz

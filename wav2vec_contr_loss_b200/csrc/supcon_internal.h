@@ -34,13 +34,15 @@ cudaError_t ffma_topk_indices(const FfmaArgs& a, int32_t* idx_out, cudaStream_t 
 struct TcPlan {
   int n_pad, rows_pad, row_blocks, fwd_row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_splits, bwd_splits, merge_blocks;
   size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
-      off_scalars, off_part, total_bytes;
+      off_scalars, off_topk_v, off_topk_i, off_part, total_bytes;
 };
 struct TcFwdArgs {
   const int32_t* lab_pad;
   const float* nrm_pad;
-  float* part;  // [splits][rows_pad][4]
-  int n_total, n_pad, row_offset, n_rows, rows_pad, splits, col_tiles, topk;
+  float* part;       // [splits][rows_pad][8]
+  float* topk_v;     // [splits][rows_pad][kcap]  per-split hard-negative candidates (mining)
+  int32_t* topk_i;
+  int n_total, n_pad, row_offset, n_rows, rows_pad, splits, col_tiles, topk, mine, kcap;
   float inv_tau, c1, c0, ut2;
 };
 struct TcBwdPrepArgs {
@@ -57,6 +59,8 @@ struct TcBwdArgs {
   const int32_t* lab_pad;
   const float* nrm_pad;
   const float *colA, *colB;
+  const float *colAm, *colThr;   // mining
+  const int32_t* colThrIdx;
   const float* scalars;  // [0] = uniformity coefficient cu
   float* dz_part;        // [splits][rows_pad][256]
   int n_total, n_pad, row_offset, n_rows, rows_pad, splits, col_tiles;

@@ -127,13 +127,37 @@ __global__ void tc_prep_bwd_kernel(TcBwdPrepArgs a) {
 struct RowSums {
   float sum_all, sum_pos_s, wsum;
   int npos;
+  float sum_pos_e;   // mining: sum of e over positives
 };
 
-template <int SIM, bool UNI, bool MASKED>
+constexpr int TC_KCAP = 32;      // in-sweep list capacity per row on the tensor path
+constexpr int LIST_STRIDE = 256; // lists are interleaved over the 256 softmax threads (conflict-free)
+
+// Sorted insert, order (value desc, index asc).  Columns reach a thread in ascending index order and a
+// candidate must be strictly greater than the current K-th value, so ties keep the lower index.
+struct MineState {
+  float thr;  // K-th best value once the list is full, -inf before
+  int cnt;
+};
+__device__ __noinline__ void mine_insert(float* lv, int* li, int K, MineState& st, float s, int gj) {
+  int p;
+  if (st.cnt < K) p = st.cnt++;
+  else p = K - 1;
+  while (p > 0 && lv[(p - 1) * LIST_STRIDE] < s) {
+    lv[p * LIST_STRIDE] = lv[(p - 1) * LIST_STRIDE];
+    li[p * LIST_STRIDE] = li[(p - 1) * LIST_STRIDE];
+    --p;
+  }
+  lv[p * LIST_STRIDE] = s;
+  li[p * LIST_STRIDE] = gj;
+  st.thr = (st.cnt >= K) ? lv[(K - 1) * LIST_STRIDE] : -INFINITY;
+}
+
+template <int SIM, bool UNI, bool MINE, bool MASKED>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int gi, int n_total, int lab_r,
                                           float nrm_r, const int32_t* __restrict__ lab_s,
                                           const float* __restrict__ nrm_s, float c1, float c0, float ut2,
-                                          RowSums& st) {
+                                          RowSums& st, MineState& ms, float* lv, int* li, int K) {
   // lab_s / nrm_s: this chunk's 32 column labels / squared norms in shared memory (broadcast reads)
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -148,14 +172,22 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
       const float s = (SIM == SUPCON_GEODESIC) ? geodesic_sim_fast(c) : c;
       float ex = ex2f(fmaf(s, c1, c0));
       bool pos = labs[e] == lab_r;
+      bool neg = !pos;
       if (MASKED) {
         const int gj = gj0 + 4 * q + e;
         const bool valid = gj < n_total && gj != gi;
         ex = valid ? ex : 0.f;
         pos = pos && valid;
+        neg = neg && valid;
       }
       st.sum_all += ex;
-      if (pos) { st.sum_pos_s += s; st.npos++; }
+      if (pos) {
+        st.sum_pos_s += s; st.npos++;
+        if (MINE) st.sum_pos_e += ex;
+      }
+      if (MINE) {
+        if (neg && s > ms.thr) mine_insert(lv, li, K, ms, s, gj0 + 4 * q + e);
+      }
       if (UNI) {
         float w = ex2f(-ut2 * fmaxf(nrm_r + njs[e] - 2.f * c, 0.f));
         if (MASKED) {
@@ -191,13 +223,13 @@ __device__ __forceinline__ void load_rows_to_tmem(const __nv_bfloat16* __restric
 // row blocks live in tensor memory as the MMA A operands.  Warpgroup g drains S_g:
 // it pulls the whole 128x128 tile into registers, releases the TMEM buffer at once
 // (the next MMA into it overlaps the exp work) and then reduces from registers.
-template <int SIM, bool UNI>
+template <int SIM, bool UNI, bool MINE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
                                                              const __nv_bfloat16* __restrict__ z, TcFwdArgs a) {
   constexpr int BN = 128;
   constexpr uint32_t BOX_BYTES = 128 * 128;          // 128 rows x 128 B
   constexpr uint32_t TILE_BYTES = NBOX * BOX_BYTES;  // 64 KB
-  constexpr int STAGES = 3;
+  constexpr int STAGES = MINE ? 2 : 3;               // mining: the third stage's 64 KB hold the top-K lists
   constexpr uint32_t TM_A = 0, TM_S = 256;           // A_g at 128 g, S_g at 256 + 128 g
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sZJ = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -289,6 +321,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
     const int rblk0 = row0 + wg * TBM;
     RowSums st;
     st.sum_all = 0.f; st.sum_pos_s = 0.f; st.wsum = 0.f; st.npos = 0;
+    st.sum_pos_e = 0.f;
+    MineState ms;
+    ms.thr = -INFINITY; ms.cnt = 0;
+    const int tslot = (warp - 2) * 32 + lane;
+    float* lv = reinterpret_cast<float*>(sZJ + STAGES * TILE_BYTES) + tslot;   // [TC_KCAP][256] values
+    int* li = reinterpret_cast<int*>(lv - tslot + TC_KCAP * LIST_STRIDE) + tslot;  // [TC_KCAP][256] indices
+    const int K = a.kcap;
     const uint32_t taddr = tmem + lane_addr + TM_S + wg * BN;
     for (int t = 0; t < ntiles; ++t) {
       const int slot = t % RING;
@@ -308,20 +347,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
       const int32_t* lab_s = lab_ring[slot];
       const float* nrm_s = nrm_ring[UNI ? slot : 0];
       if (masked) {
-        fwd_chunk<SIM, UNI, true>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st);
-        fwd_chunk<SIM, UNI, true>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st);
-        fwd_chunk<SIM, UNI, true>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st);
-        fwd_chunk<SIM, UNI, true>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st);
+        fwd_chunk<SIM, UNI, MINE, true>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+        fwd_chunk<SIM, UNI, MINE, true>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+        fwd_chunk<SIM, UNI, MINE, true>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+        fwd_chunk<SIM, UNI, MINE, true>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
       } else {
-        fwd_chunk<SIM, UNI, false>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st);
-        fwd_chunk<SIM, UNI, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st);
-        fwd_chunk<SIM, UNI, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st);
-        fwd_chunk<SIM, UNI, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st);
+        fwd_chunk<SIM, UNI, MINE, false>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+        fwd_chunk<SIM, UNI, MINE, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+        fwd_chunk<SIM, UNI, MINE, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+        fwd_chunk<SIM, UNI, MINE, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
       }
     }
     if (gi < a.row_offset + a.n_rows) {
-      float* out = a.part + ((int64_t)split * a.rows_pad + (gi - a.row_offset)) * 4;
+      const int64_t rec = (int64_t)split * a.rows_pad + (gi - a.row_offset);
+      float* out = a.part + rec * 8;
       *reinterpret_cast<float4*>(out) = make_float4(st.sum_all, st.sum_pos_s, st.wsum, __int_as_float(st.npos));
+      *reinterpret_cast<float4*>(out + 4) = make_float4(st.sum_pos_e, __int_as_float(ms.cnt), 0.f, 0.f);
+      if (MINE) {
+        for (int e = 0; e < ms.cnt; ++e) {
+          a.topk_v[rec * K + e] = lv[e * LIST_STRIDE];
+          a.topk_i[rec * K + e] = li[e * LIST_STRIDE];
+        }
+      }
     }
   }
   ptx::tc_fence_before_sync();
@@ -336,27 +383,59 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
   const int lr = blockIdx.x * 128 + threadIdx.x;
   double l_full = 0.0, c_full = 0.0, l_mined = 0.0, c_mined = 0.0, w = 0.0;
   if (lr < a.n_rows) {
-    float sum_all = 0.f, sum_pos_s = 0.f, wsum = 0.f;
+    float sum_all = 0.f, sum_pos_s = 0.f, wsum = 0.f, sum_pos_e = 0.f;
     int npos = 0;
     for (int s = 0; s < a.splits; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(a.part + ((int64_t)s * a.rows_pad + lr) * 4);
+      const float* rec = a.part + ((int64_t)s * a.rows_pad + lr) * 8;
+      const float4 v = *reinterpret_cast<const float4*>(rec);
       sum_all += v.x; sum_pos_s += v.y; wsum += v.z; npos += __float_as_int(v.w);
+      sum_pos_e += rec[4];
     }
     const int nneg = a.n_total - 1 - npos;
     const float lse = logf(sum_all) + a.inv_tau;   // fixed maximum 1/tau folded back in
     const float pos_mean = npos > 0 ? (sum_pos_s * a.inv_tau) / (float)npos : 0.f;
+    float lse_m = lse;
+    float thr_val = a.topk >= 1 ? -INFINITY : INFINITY;
+    int thr_idx = a.topk >= 1 ? SUPCON_INT_MAX : -1;
+    if (a.mine && nneg > a.topk) {
+      // merge the per-split top-K lists (splits cover ascending column ranges, each list is sorted by
+      // (value desc, index asc)): insertion with a strict compare keeps that order globally
+      const int K = a.kcap;
+      float mv[TC_KCAP];
+      int mi[TC_KCAP];
+      int cnt = 0;
+      for (int s = 0; s < a.splits; ++s) {
+        const int64_t rec = (int64_t)s * a.rows_pad + lr;
+        const int c = __float_as_int(a.part[rec * 8 + 5]);
+        for (int e = 0; e < c; ++e) {
+          const float v = a.topk_v[rec * K + e];
+          const int ix = a.topk_i[rec * K + e];
+          int p;
+          if (cnt < K) p = cnt++;
+          else if (v > mv[K - 1]) p = K - 1;
+          else break;   // this list is sorted: nothing further down can enter
+          while (p > 0 && mv[p - 1] < v) { mv[p] = mv[p - 1]; mi[p] = mi[p - 1]; --p; }
+          mv[p] = v; mi[p] = ix;
+        }
+      }
+      float sum_top = 0.f;
+      for (int e = 0; e < K; ++e) sum_top += ex2f(fmaf(mv[e], a.c1, a.c0));
+      lse_m = logf(sum_pos_e + sum_top) + a.inv_tau;
+      thr_val = mv[K - 1];
+      thr_idx = mi[K - 1];
+    }
     float* so = row_stats + (int64_t)lr * SUPCON_STATS_STRIDE;
     so[SUPCON_ST_LSE] = lse;
-    so[SUPCON_ST_LSE_M] = lse;
+    so[SUPCON_ST_LSE_M] = lse_m;
     reinterpret_cast<int*>(so)[SUPCON_ST_NPOS] = npos;
     reinterpret_cast<int*>(so)[SUPCON_ST_NNEG] = nneg;
-    so[SUPCON_ST_THR_VAL] = a.topk >= 1 ? -INFINITY : INFINITY;
-    reinterpret_cast<int*>(so)[SUPCON_ST_THR_IDX] = a.topk >= 1 ? SUPCON_INT_MAX : -1;
+    so[SUPCON_ST_THR_VAL] = thr_val;
+    reinterpret_cast<int*>(so)[SUPCON_ST_THR_IDX] = thr_idx;
     so[SUPCON_ST_WSUM] = wsum;
     so[SUPCON_ST_POS_MEAN] = pos_mean;
     if (npos > 0) {
       l_full = (double)(lse - pos_mean); c_full = 1.0;
-      if (nneg > 0 && a.topk >= 1) { l_mined = l_full; c_mined = 1.0; }
+      if (nneg > 0 && a.topk >= 1) { l_mined = (double)(lse_m - pos_mean); c_mined = 1.0; }
     }
     w = (double)wsum;
   }
@@ -372,12 +451,18 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
 struct ColVecs {  // this chunk's 32 column entries in shared memory
   const int32_t* lab;
   const float *A, *B, *nrm;
+  const float *Am, *thr;   // mining: a_m exp(1/tau - lse_m) and threshold value of the column's own row
+  const int32_t* thr_idx;
+};
+struct RowMine {  // the same for this thread's row
+  float Am, thr;
+  int thr_idx;
 };
 
-template <int SIM, bool UNI, bool MASKED>
+template <int SIM, bool UNI, bool MINE, bool MASKED>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw)[16], int gj0, int gi, int lab_r,
                                           float A_r, float B_r, float nrm_r, float cu, const ColVecs& cv,
-                                          const TcBwdArgs& a) {
+                                          const RowMine& rm, const TcBwdArgs& a) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int4 lb = *reinterpret_cast<const int4*>(cv.lab + 4 * q);
@@ -389,6 +474,16 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw
     const float As[4] = {Aj.x, Aj.y, Aj.z, Aj.w};
     const float Bs[4] = {Bj.x, Bj.y, Bj.z, Bj.w};
     const float njs[4] = {nj.x, nj.y, nj.z, nj.w};
+    float4 Amj = make_float4(0.f, 0.f, 0.f, 0.f), Tj = Amj;
+    int4 Ij = make_int4(0, 0, 0, 0);
+    if (MINE) {
+      Amj = *reinterpret_cast<const float4*>(cv.Am + 4 * q);
+      Tj = *reinterpret_cast<const float4*>(cv.thr + 4 * q);
+      Ij = *reinterpret_cast<const int4*>(cv.thr_idx + 4 * q);
+    }
+    const float Ams[4] = {Amj.x, Amj.y, Amj.z, Amj.w};
+    const float Ts[4] = {Tj.x, Tj.y, Tj.z, Tj.w};
+    const int Is[4] = {Ij.x, Ij.y, Ij.z, Ij.w};
     float h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -396,6 +491,14 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw
       const float s = (SIM == SUPCON_GEODESIC) ? geodesic_sim_fast(c) : c;
       const float e0 = ex2f(fmaf(s, a.c1, a.c0));
       float v = e0 * (A_r + As[e]);
+      if (MINE) {
+        // j in pos_i U top_i  /  i in pos_j U top_j, re-derived from the stored thresholds
+        const int gj = gj0 + 4 * q + e;
+        const bool pos = labs[e] == lab_r;
+        const bool mem_r = pos || s > rm.thr || (s == rm.thr && gj <= rm.thr_idx);
+        const bool mem_c = pos || s > Ts[e] || (s == Ts[e] && gi <= Is[e]);
+        v = fmaf(e0, (mem_r ? rm.Am : 0.f) + (mem_c ? Ams[e] : 0.f), v);
+      }
       if (labs[e] == lab_r) v -= B_r + Bs[e];
       if (SIM == SUPCON_GEODESIC) v *= geodesic_slope_fast(c);
       if (UNI) v = fmaf(-cu, ex2f(-a.ut2 * fmaxf(nrm_r + njs[e] - 2.f * c, 0.f)), v);
@@ -415,7 +518,7 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw
 // buffer, from where it is the A operand of dZ += H Z_J (no shared-memory round trip).
 // Tensor-pipe order: S(0) S(1) dZ(0) S(2) dZ(1) ...; tcgen05.mma executes in issue order,
 // so S(t+2) cannot overwrite the buffer dZ(t) is still reading.
-template <int SIM, bool UNI>
+template <int SIM, bool UNI, bool MINE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapJ,
                                                              const __nv_bfloat16* __restrict__ z, TcBwdArgs a) {
   constexpr int BN = 64;
@@ -432,6 +535,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   __shared__ __align__(16) int32_t lab_ring[RING][BN];
   __shared__ __align__(16) float colA_ring[RING][BN], colB_ring[RING][BN];
   __shared__ __align__(16) float nrm_ring[UNI ? RING : 1][BN];
+  __shared__ __align__(16) float colAm_ring[MINE ? RING : 1][BN], thr_ring[MINE ? RING : 1][BN];
+  __shared__ __align__(16) int32_t thridx_ring[MINE ? RING : 1][BN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rb = blockIdx.x / a.splits, split = blockIdx.x % a.splits;
@@ -479,6 +584,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
         if (UNI)
           *reinterpret_cast<float4*>(&nrm_ring[slot][4 * l]) =
               __ldg(reinterpret_cast<const float4*>(a.nrm_pad + col0 + 4 * l));
+      }
+      if (MINE) {
+        if (lane < 16) {
+          *reinterpret_cast<float4*>(&colAm_ring[slot][4 * lane]) =
+              __ldg(reinterpret_cast<const float4*>(a.colAm + col0 + 4 * lane));
+          *reinterpret_cast<int4*>(&thridx_ring[slot][4 * lane]) =
+              __ldg(reinterpret_cast<const int4*>(a.colThrIdx + col0 + 4 * lane));
+        } else {
+          const int l = lane - 16;
+          *reinterpret_cast<float4*>(&thr_ring[slot][4 * l]) =
+              __ldg(reinterpret_cast<const float4*>(a.colThr + col0 + 4 * l));
+        }
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar_col[slot]);
@@ -535,6 +652,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
     const float A_r = a.colA[gic], B_r = a.colB[gic];
     const float nrm_r = UNI ? a.nrm_pad[gic] : 0.f;
     const float cu = UNI ? a.scalars[0] : 0.f;
+    RowMine rm;
+    rm.Am = MINE ? a.colAm[gic] : 0.f; rm.thr = MINE ? a.colThr[gic] : 0.f; rm.thr_idx = MINE ? a.colThrIdx[gic] : 0;
     const uint32_t sbuf = tmem + lane_addr + TM_S + wg * BN;
     for (int t = wg; t < ntiles; t += 2) {
       const int buse = t >> 1, slot = t % RING;
@@ -551,14 +670,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       uint32_t (&h1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[16]);
       ColVecs cv0, cv1;
       cv0.lab = lab_ring[slot]; cv0.A = colA_ring[slot]; cv0.B = colB_ring[slot]; cv0.nrm = nrm_ring[UNI ? slot : 0];
+      cv0.Am = colAm_ring[MINE ? slot : 0]; cv0.thr = thr_ring[MINE ? slot : 0]; cv0.thr_idx = thridx_ring[MINE ? slot : 0];
       cv1.lab = cv0.lab + 32; cv1.A = cv0.A + 32; cv1.B = cv0.B + 32; cv1.nrm = cv0.nrm + 32;
+      cv1.Am = cv0.Am + 32; cv1.thr = cv0.thr + 32; cv1.thr_idx = cv0.thr_idx + 32;
       const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
       if (masked) {
-        bwd_chunk<SIM, UNI, true>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, a);
-        bwd_chunk<SIM, UNI, true>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, a);
+        bwd_chunk<SIM, UNI, MINE, true>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, rm, a);
+        bwd_chunk<SIM, UNI, MINE, true>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, rm, a);
       } else {
-        bwd_chunk<SIM, UNI, false>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, a);
-        bwd_chunk<SIM, UNI, false>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, a);
+        bwd_chunk<SIM, UNI, MINE, false>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, rm, a);
+        bwd_chunk<SIM, UNI, MINE, false>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, rm, a);
       }
       ptx::tmem_st32(sbuf, hw);            // H(t): 64 bf16 = 32 packed columns over S(t)
       ptx::tmem_st_wait();
@@ -686,8 +807,12 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.off_colThr = off; off += align_up((size_t)pl.n_pad * 4, 256);
   pl.off_colThrIdx = off; off += align_up((size_t)pl.n_pad * 4, 256);
   pl.off_scalars = off; off += 256;
+  const bool mine = p->alpha != 0.f && p->topk >= 1;
+  const size_t kcap = mine ? (size_t)(p->topk < TC_KCAP ? p->topk : TC_KCAP) : 0;
+  pl.off_topk_v = off; off += align_up((size_t)pl.fwd_splits * pl.rows_pad * kcap * 4, 256);
+  pl.off_topk_i = off; off += align_up((size_t)pl.fwd_splits * pl.rows_pad * kcap * 4, 256);
   pl.off_part = off;
-  size_t fwd_part = (size_t)pl.fwd_splits * pl.rows_pad * 4 * sizeof(float);
+  size_t fwd_part = (size_t)pl.fwd_splits * pl.rows_pad * 8 * sizeof(float);
   size_t bwd_part = (size_t)pl.bwd_splits * pl.rows_pad * TD * sizeof(float);
   off += align_up(fwd_part > bwd_part ? fwd_part : bwd_part, 256);
   pl.total_bytes = off;
@@ -697,18 +822,24 @@ TcPlan tc_plan(const supcon_problem_t* p) {
 bool tc_supported(const supcon_problem_t* p) {
   if (p->z_dtype != SUPCON_BF16 || p->d != TD) return false;
   if (!(p->tau >= 0.025f)) return false;
-  if (p->alpha != 0.f && p->topk >= 1) return false;   // hard-negative mining: exact path for now
+  if (p->alpha != 0.f && p->topk > TC_KCAP) return false;   // in-sweep top-K lists hold at most 32 entries
   if (p->n_total < 256) return false;
   return true;
 }
 
-template <int SIM, bool UNI>
+template <int SIM, bool UNI, bool MINE>
 static cudaError_t launch_fwd(const CUtensorMap& tm, const __nv_bfloat16* z, const TcFwdArgs& a, int ctas, size_t smem,
                               cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<SIM, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e =
+      cudaFuncSetAttribute(tc_fwd_kernel<SIM, UNI, MINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_fwd_kernel<SIM, UNI><<<ctas, NTHREADS, smem, st>>>(tm, z, a);
+  tc_fwd_kernel<SIM, UNI, MINE><<<ctas, NTHREADS, smem, st>>>(tm, z, a);
   return cudaGetLastError();
+}
+template <int SIM, bool UNI>
+static cudaError_t launch_fwd_m(bool mine, const CUtensorMap& tm, const __nv_bfloat16* z, const TcFwdArgs& a, int ctas,
+                                size_t smem, cudaStream_t st) {
+  return mine ? launch_fwd<SIM, UNI, true>(tm, z, a, ctas, smem, st) : launch_fwd<SIM, UNI, false>(tm, z, a, ctas, smem, st);
 }
 
 int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, float* row_stats,
@@ -739,14 +870,19 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
   a.rows_pad = pl.rows_pad; a.splits = pl.fwd_splits; a.col_tiles = pl.fwd_col_tiles; a.topk = p->topk;
   a.inv_tau = 1.0f / p->tau;
   a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
-  const size_t smem = 3 * (size_t)NBOX * 128 * 128 + 1024;
+  const bool mine = p->alpha != 0.f && p->topk >= 1;
+  a.mine = mine ? 1 : 0;
+  a.kcap = mine ? (p->topk < TC_KCAP ? p->topk : TC_KCAP) : 0;
+  a.topk_v = reinterpret_cast<float*>(ws + pl.off_topk_v);
+  a.topk_i = reinterpret_cast<int32_t*>(ws + pl.off_topk_i);
+  const size_t smem = 3 * (size_t)NBOX * 128 * 128 + 1024;   // 3 tile stages, or 2 stages + 64 KB of top-K lists
   const int ctas = pl.fwd_row_blocks * pl.fwd_splits;
   const bool geo = p->similarity == SUPCON_GEODESIC;
   const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
-  if (geo && uni) e = launch_fwd<SUPCON_GEODESIC, true>(tm, zb, a, ctas, smem, stream);
-  else if (geo) e = launch_fwd<SUPCON_GEODESIC, false>(tm, zb, a, ctas, smem, stream);
-  else if (uni) e = launch_fwd<SUPCON_COSINE, true>(tm, zb, a, ctas, smem, stream);
-  else e = launch_fwd<SUPCON_COSINE, false>(tm, zb, a, ctas, smem, stream);
+  if (geo && uni) e = launch_fwd_m<SUPCON_GEODESIC, true>(mine, tm, zb, a, ctas, smem, stream);
+  else if (geo) e = launch_fwd_m<SUPCON_GEODESIC, false>(mine, tm, zb, a, ctas, smem, stream);
+  else if (uni) e = launch_fwd_m<SUPCON_COSINE, true>(mine, tm, zb, a, ctas, smem, stream);
+  else e = launch_fwd_m<SUPCON_COSINE, false>(mine, tm, zb, a, ctas, smem, stream);
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
   FinishArgs f{reinterpret_cast<double*>(ws + pl.off_block_partials), reinterpret_cast<unsigned*>(ws), partials,
                loss_out, p->n_total, p->tau, p->alpha, p->lambda_uni, p->uni_t};
@@ -756,13 +892,19 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
   return 0;
 }
 
-template <int SIM, bool UNI>
+template <int SIM, bool UNI, bool MINE>
 static cudaError_t launch_bwd(const CUtensorMap& tmJ, const __nv_bfloat16* z, const TcBwdArgs& a, int ctas, size_t smem,
                               cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<SIM, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e =
+      cudaFuncSetAttribute(tc_bwd_kernel<SIM, UNI, MINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_bwd_kernel<SIM, UNI><<<ctas, NTHREADS, smem, st>>>(tmJ, z, a);
+  tc_bwd_kernel<SIM, UNI, MINE><<<ctas, NTHREADS, smem, st>>>(tmJ, z, a);
   return cudaGetLastError();
+}
+template <int SIM, bool UNI>
+static cudaError_t launch_bwd_m(bool mine, const CUtensorMap& tmJ, const __nv_bfloat16* z, const TcBwdArgs& a, int ctas,
+                                size_t smem, cudaStream_t st) {
+  return mine ? launch_bwd<SIM, UNI, true>(tmJ, z, a, ctas, smem, st) : launch_bwd<SIM, UNI, false>(tmJ, z, a, ctas, smem, st);
 }
 
 int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, const float* stats_all,
@@ -800,6 +942,7 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   TcBwdArgs a;
   a.lab_pad = pa.lab_pad; a.nrm_pad = reinterpret_cast<const float*>(ws + pl.off_nrm);
   a.colA = pa.colA; a.colB = pa.colB;
+  a.colAm = pa.colAm; a.colThr = pa.colThr; a.colThrIdx = pa.colThrIdx;
   a.dz_part = reinterpret_cast<float*>(ws + pl.off_part);
   a.n_total = p->n_total; a.n_pad = pl.n_pad; a.row_offset = p->row_offset; a.n_rows = p->n_rows;
   a.rows_pad = pl.rows_pad; a.splits = pl.bwd_splits; a.col_tiles = pl.bwd_col_tiles;
@@ -809,10 +952,11 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   const int ctas = pl.row_blocks * pl.bwd_splits;
   const bool geo = p->similarity == SUPCON_GEODESIC;
   const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
-  if (geo && uni) e = launch_bwd<SUPCON_GEODESIC, true>(tmJ, zb, a, ctas, smem, stream);
-  else if (geo) e = launch_bwd<SUPCON_GEODESIC, false>(tmJ, zb, a, ctas, smem, stream);
-  else if (uni) e = launch_bwd<SUPCON_COSINE, true>(tmJ, zb, a, ctas, smem, stream);
-  else e = launch_bwd<SUPCON_COSINE, false>(tmJ, zb, a, ctas, smem, stream);
+  const bool mine = p->alpha != 0.f && p->topk >= 1;
+  if (geo && uni) e = launch_bwd_m<SUPCON_GEODESIC, true>(mine, tmJ, zb, a, ctas, smem, stream);
+  else if (geo) e = launch_bwd_m<SUPCON_GEODESIC, false>(mine, tmJ, zb, a, ctas, smem, stream);
+  else if (uni) e = launch_bwd_m<SUPCON_COSINE, true>(mine, tmJ, zb, a, ctas, smem, stream);
+  else e = launch_bwd_m<SUPCON_COSINE, false>(mine, tmJ, zb, a, ctas, smem, stream);
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
   const int64_t n4 = (int64_t)p->n_rows * (TD / 4);
   const int blocks = (int)((n4 + 255) / 256);

@@ -3,10 +3,10 @@
 Rank r holds the embeddings/labels of its local batch = rows
 [r*n_local, (r+1)*n_local) of the global N x N similarity matrix:
 
-  forward   all_gather(z), all_gather(labels)            (NVLink, NCCL)
+  forward   all_gather(z) + all_gather(labels)          (one coalesced NCCL launch over NVLink)
             row-block forward kernel  -> row stats + 8 partial sums
-            all_reduce(partials)      -> scalar loss (identical on every rank)
-            all_gather(row stats)     (N x 32 B; needed by the backward)
+            all_reduce(partials) + all_gather(row stats, N x 32 B)   (one coalesced launch)
+            -> scalar loss (identical on every rank)
   backward  row-block backward kernel: dz_i = sum_j (G_ij + G_ji) z_j for the
             owned rows, recomputing the tiles.  Because the similarity matrix
             is symmetric the column-side term G_ji only needs the *statistics*
@@ -53,21 +53,53 @@ def _all_gather_rows(x: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
+def _coalesced(group, device):
+    """One NCCL group launch for the collectives issued inside the block (falls back to
+    plain sequential collectives on backends without coalescing support, e.g. gloo)."""
+    import contextlib
+    mgr = getattr(dist, "_coalescing_manager", None)
+    if mgr is None or device.type != "cuda":
+        return contextlib.nullcontext()
+    return mgr(group=group, device=device, async_ops=False)
+
+
+def gather_inputs(z_local: torch.Tensor, labels_local: torch.Tensor, group=None):
+    """all-gather of embeddings and labels in ONE collective launch. Returns (z_all, labels_all)."""
+    world = dist.get_world_size(group)
+    z_all = torch.empty((world * z_local.size(0), z_local.size(1)), dtype=z_local.dtype, device=z_local.device)
+    y_all = torch.empty(world * labels_local.size(0), dtype=labels_local.dtype, device=labels_local.device)
+    with _coalesced(group, z_local.device):
+        dist.all_gather_into_tensor(z_all, z_local.contiguous(), group=group)
+        dist.all_gather_into_tensor(y_all, labels_local.contiguous(), group=group)
+    return z_all, y_all
+
+
+def exchange_stats(partials: torch.Tensor, stats: torch.Tensor, group=None):
+    """all-reduce of the 8 partial sums + all-gather of the row statistics in ONE collective launch."""
+    world = dist.get_world_size(group)
+    stats_all = torch.empty((world * stats.size(0),) + tuple(stats.shape[1:]), dtype=stats.dtype, device=stats.device)
+    with _coalesced(group, stats.device):
+        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+        dist.all_gather_into_tensor(stats_all, stats.contiguous(), group=group)
+    return stats_all
+
+
 class _ShardedSupCon(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z_local, labels_local, cfg, group, kernels):
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         zc = Fn.canonical_z(z_local.detach())
         n_local, d = zc.shape
-        z_all = _all_gather_rows(zc, group)
-        labels_all = _all_gather_rows(labels_local, group)
+        z_all, labels_all = gather_inputs(zc, labels_local, group)
         prob = Fn.make_problem(n_local * world, d, Fn._dtype_id(zc), row_offset=rank * n_local, n_rows=n_local,
                                **cfg)
         stats, partials = kernels.forward_rows(z_all, labels_all, prob)
-        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+        if ctx.needs_input_grad[0]:
+            stats_all = exchange_stats(partials, stats, group)
+        else:
+            dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
         loss = kernels.finalize(prob, partials)
         if ctx.needs_input_grad[0]:
-            stats_all = _all_gather_rows(stats, group)
             ctx.save_for_backward(z_all, labels_all, stats_all, partials)
             ctx.prob, ctx.kernels, ctx.in_dtype, ctx.work_dtype = prob, kernels, z_local.dtype, zc.dtype
         return Fn._loss_dtype(loss, z_local.dtype)
