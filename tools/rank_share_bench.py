@@ -34,6 +34,25 @@ for R in ranks:
         e[2].record(); torch.cuda.synchronize()
         fw += e[0].elapsed_time(e[1]); bw += e[1].elapsed_time(e[2])
     fw /= iters; bw /= iters
+    # whole rank step as one CUDA graph (no host launch gaps)
+    gms = None
+    try:
+        gr = torch.cuda.CUDAGraph(); side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        def both():
+            st_, pa_, _ = Fn.forward_rows(z, y, prob, want_loss=False)
+            return Fn.backward_rows(z, y, stats_all, partials, None, prob, out_dtype=torch.bfloat16)
+        with torch.cuda.stream(side):
+            both(); torch.cuda.synchronize()
+            with torch.cuda.graph(gr, stream=side):
+                both()
+        torch.cuda.synchronize()
+        for _ in range(3): gr.replay()
+        e[0].record()
+        for _ in range(iters): gr.replay()
+        e[1].record(); torch.cuda.synchronize()
+        gms = e[0].elapsed_time(e[1]) / iters
+    except Exception as ex:  # noqa: BLE001
+        gms = str(ex)
     fl = 6.0 * n * nl * 256
-    print(json.dumps(dict(N=n, R=R, rows=nl, fwd_ms=round(fw, 4), bwd_ms=round(bw, 4), tflops=round(fl / (fw + bw) / 1e9, 1),
+    print(json.dumps(dict(N=n, R=R, rows=nl, fwd_ms=round(fw, 4), bwd_ms=round(bw, 4), graph_ms=(round(gms, 4) if isinstance(gms, float) else gms), graph_tflops=(round(fl / gms / 1e9, 1) if isinstance(gms, float) else None), tflops=round(fl / (fw + bw) / 1e9, 1),
                           env={k: v for k, v in os.environ.items() if k.startswith("SUPCON_")})), flush=True)

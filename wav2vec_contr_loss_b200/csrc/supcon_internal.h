@@ -31,7 +31,13 @@ cudaError_t ffma_backward(const FfmaArgs& a, int dz_dtype, cudaStream_t stream);
 cudaError_t ffma_topk_indices(const FfmaArgs& a, int32_t* idx_out, cudaStream_t stream);
 
 // ---- bf16 tensor-core path (supcon_tc.cu) ----
+struct TcSched {   // flattened (row block, column tile) work list cut into P contiguous CTA ranges
+  int T;           // column tiles per row block
+  int P;           // CTAs
+  long long U;     // row_blocks * T
+};
 struct TcPlan {
+  TcSched fwd_sched, bwd_sched;
   int n_pad, rows_pad, row_blocks, fwd_row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_splits, bwd_splits, merge_blocks;
   size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
       off_scalars, off_topk_v, off_topk_i, off_part, total_bytes;
@@ -42,7 +48,8 @@ struct TcFwdArgs {
   float* part;       // [splits][rows_pad][8]
   float* topk_v;     // [splits][rows_pad][kcap]  per-split hard-negative candidates (mining)
   int32_t* topk_i;
-  int n_total, n_pad, row_offset, n_rows, rows_pad, splits, col_tiles, topk, mine, kcap;
+  TcSched sched;
+  int n_total, n_pad, row_offset, n_rows, rows_pad, topk, mine, kcap;
   float inv_tau, c1, c0, ut2;
 };
 struct TcBwdPrepArgs {
@@ -63,7 +70,8 @@ struct TcBwdArgs {
   const int32_t* colThrIdx;
   const float* scalars;  // [0] = uniformity coefficient cu
   float* dz_part;        // [splits][rows_pad][256]
-  int n_total, n_pad, row_offset, n_rows, rows_pad, splits, col_tiles;
+  TcSched sched;
+  int n_total, n_pad, row_offset, n_rows, rows_pad;
   float c1, c0, ut2;
 };
 TcPlan tc_plan(const supcon_problem_t* p);

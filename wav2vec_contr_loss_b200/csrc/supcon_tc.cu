@@ -122,6 +122,21 @@ __global__ void tc_prep_bwd_kernel(TcBwdPrepArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// work distribution: the (row block, column tile) grid is flattened row-major into U = RB * T
+// units and cut into P contiguous ranges, one per CTA (P = #SMs: a single, balanced wave).  A range
+// touches at most a few row blocks ("segments"); the CTA writes one partial record per segment into
+// slot (cta - first cta touching that row block), which the merge/reduce kernels sum in slot order.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline long long sched_begin(const TcSched& s, int c) { return ((long long)c * s.U) / s.P; }
+__host__ __device__ inline int sched_cta_of(const TcSched& s, long long u) {
+  int c = (int)((u * s.P) / s.U);
+  if (c > s.P - 1) c = s.P - 1;
+  while (c + 1 < s.P && sched_begin(s, c + 1) <= u) ++c;
+  while (c > 0 && sched_begin(s, c) > u) --c;
+  return c;
+}
+
+// ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
 struct RowSums {
@@ -218,11 +233,14 @@ __device__ __forceinline__ void load_rows_to_tmem(const __nv_bfloat16* __restric
   ptx::tmem_st_wait();
 }
 
-// Forward: one CTA owns TWO 128-row blocks (a, b) that share every Z_J tile, so each
-// byte staged by TMA feeds two MMAs (halves the shared-memory traffic per flop); the
-// row blocks live in tensor memory as the MMA A operands.  Warpgroup g drains S_g:
-// it pulls the whole 128x128 tile into registers, releases the TMEM buffer at once
-// (the next MMA into it overlaps the exp work) and then reduces from registers.
+// Forward: a persistent CTA walks a contiguous range of the flattened (row-block, column-tile)
+// work list (TcSched), i.e. a few *segments* = (256-row block, column-tile range).  Per segment it
+// owns TWO 128-row blocks (a, b) that share every Z_J tile, so each byte staged by TMA feeds two
+// MMAs (halves the shared-memory traffic per flop); the row blocks live in tensor memory as the
+// MMA A operands.  Warpgroup g drains S_g: it pulls the whole 128x128 tile into registers,
+// releases the TMEM buffer at once (the next MMA into it overlaps the exp work) and then reduces
+// from registers.  All pipeline barriers are indexed by a running tile counter, so segments
+// follow each other without draining the TMA ring.
 template <int SIM, bool UNI, bool MINE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
                                                              const __nv_bfloat16* __restrict__ z, TcFwdArgs a) {
@@ -244,11 +262,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
   __shared__ __align__(16) float nrm_ring[UNI ? RING : 1][BN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rb = blockIdx.x / a.splits, split = blockIdx.x % a.splits;
-  const int row0 = a.row_offset + rb * (2 * TBM);
-  const int ct_begin = (int)(((int64_t)a.col_tiles * split) / a.splits);
-  const int ct_end = (int)(((int64_t)a.col_tiles * (split + 1)) / a.splits);
-  const int ntiles = ct_end - ct_begin;
+  const TcSched sc = a.sched;
+  const long long u_begin = sched_begin(sc, blockIdx.x), u_end = sched_begin(sc, blockIdx.x + 1);
 
   if (tid == 0) {
     ptx::mbar_init(&bar_a, 256);
@@ -266,116 +281,135 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer (lane 0) + column label/norm staging (all lanes) =====
-    for (int t = 0; t < ntiles; ++t) {
-      const int st = t % STAGES, use = t / STAGES, slot = t % RING;
-      const int col0 = (ct_begin + t) * BN;
-      ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
-      if (ptx::elect_one()) {
-        ptx::mbar_expect_tx(&bar_full[st], TILE_BYTES);
-        for (int b = 0; b < NBOX; ++b)
-          ptx::tma_load_2d(sZJ + st * TILE_BYTES + b * BOX_BYTES, &tmap, &bar_full[st], 64 * b, col0);
+    int g = 0;  // running tile counter
+    for (long long u = u_begin; u < u_end;) {
+      const int ct0 = (int)(u % sc.T);
+      const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
+      for (int t = 0; t < nt; ++t, ++g) {
+        const int st = g % STAGES, use = g / STAGES, slot = g % RING;
+        const int col0 = (ct0 + t) * BN;
+        ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&bar_full[st], TILE_BYTES);
+          for (int b = 0; b < NBOX; ++b)
+            ptx::tma_load_2d(sZJ + st * TILE_BYTES + b * BOX_BYTES, &tmap, &bar_full[st], 64 * b, col0);
+        }
+        *reinterpret_cast<int4*>(&lab_ring[slot][4 * lane]) =
+            __ldg(reinterpret_cast<const int4*>(a.lab_pad + col0 + 4 * lane));
+        if (UNI)
+          *reinterpret_cast<float4*>(&nrm_ring[slot][4 * lane]) =
+              __ldg(reinterpret_cast<const float4*>(a.nrm_pad + col0 + 4 * lane));
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar_col[slot]);
       }
-      *reinterpret_cast<int4*>(&lab_ring[slot][4 * lane]) =
-          __ldg(reinterpret_cast<const int4*>(a.lab_pad + col0 + 4 * lane));
-      if (UNI)
-        *reinterpret_cast<float4*>(&nrm_ring[slot][4 * lane]) =
-            __ldg(reinterpret_cast<const float4*>(a.nrm_pad + col0 + 4 * lane));
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar_col[slot]);
+      u += nt;
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::idesc_bf16(128, BN, false, false);
-      ptx::mbar_wait(&bar_a, 0);
-      for (int t = 0; t < ntiles; ++t) {
-        const int st = t % STAGES, use = t / STAGES;
-        ptx::mbar_wait(&bar_full[st], use & 1);
-        const uint32_t b0 = ptx::smem_u32(sZJ + st * TILE_BYTES);
+      int g = 0, seg = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        const int ct0 = (int)(u % sc.T);
+        const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
+        ptx::mbar_wait(&bar_a, seg & 1);   // this segment's row blocks are in tensor memory
+        for (int t = 0; t < nt; ++t, ++g) {
+          const int st = g % STAGES, use = g / STAGES;
+          ptx::mbar_wait(&bar_full[st], use & 1);
+          const uint32_t b0 = ptx::smem_u32(sZJ + st * TILE_BYTES);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          ptx::mbar_wait(&bar_tempty[g], (t & 1) ^ 1);
-          ptx::tc_fence_after_sync();
+          for (int w = 0; w < 2; ++w) {
+            ptx::mbar_wait(&bar_tempty[w], (g & 1) ^ 1);
+            ptx::tc_fence_after_sync();
 #pragma unroll
-          for (int ks = 0; ks < TD / 16; ++ks) {
-            const uint32_t off = (ks >> 2) * BOX_BYTES + (ks & 3) * 32;
-            ptx::mma_ts(tmem + TM_S + g * BN, tmem + TM_A + g * (TD / 2) + 8 * ks,
-                        ptx::smem_desc_sw128(b0 + off, 16, 1024), idesc, ks > 0);
+            for (int ks = 0; ks < TD / 16; ++ks) {
+              const uint32_t off = (ks >> 2) * BOX_BYTES + (ks & 3) * 32;
+              ptx::mma_ts(tmem + TM_S + w * BN, tmem + TM_A + w * (TD / 2) + 8 * ks,
+                          ptx::smem_desc_sw128(b0 + off, 16, 1024), idesc, ks > 0);
+            }
+            ptx::mma_commit(&bar_tfull[w]);
           }
-          ptx::mma_commit(&bar_tfull[g]);
+          ptx::mma_commit(&bar_empty[st]);
         }
-        ptx::mma_commit(&bar_empty[st]);
+        u += nt;
       }
     }
   } else {
     // ===== softmax warpgroups: warps 2-5 own row block a, warps 6-9 row block b =====
     const int wg = (warp - 2) >> 2;
     const int lrow = 32 * (warp & 3) + lane;  // TMEM lane == row within the block
-    const int gi = row0 + wg * TBM + lrow;
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
-    load_rows_to_tmem(z, gi, a.n_total, tmem + lane_addr + TM_A + wg * (TD / 2));
-    ptx::tc_fence_before_sync();
-    ptx::mbar_arrive(&bar_a);
-    const int lab_r = a.lab_pad[min(gi, a.n_pad - 1)];
-    const float nrm_r = UNI ? a.nrm_pad[min(gi, a.n_pad - 1)] : 0.f;
-    const int rblk0 = row0 + wg * TBM;
-    RowSums st;
-    st.sum_all = 0.f; st.sum_pos_s = 0.f; st.wsum = 0.f; st.npos = 0;
-    st.sum_pos_e = 0.f;
-    MineState ms;
-    ms.thr = -INFINITY; ms.cnt = 0;
     const int tslot = (warp - 2) * 32 + lane;
-    float* lv = reinterpret_cast<float*>(sZJ + STAGES * TILE_BYTES) + tslot;   // [TC_KCAP][256] values
+    float* lv = reinterpret_cast<float*>(sZJ + STAGES * TILE_BYTES) + tslot;       // [TC_KCAP][256] values
     int* li = reinterpret_cast<int*>(lv - tslot + TC_KCAP * LIST_STRIDE) + tslot;  // [TC_KCAP][256] indices
     const int K = a.kcap;
     const uint32_t taddr = tmem + lane_addr + TM_S + wg * BN;
-    for (int t = 0; t < ntiles; ++t) {
-      const int slot = t % RING;
-      const int col0 = (ct_begin + t) * BN;
-      ptx::mbar_wait(&bar_col[slot], (t / RING) & 1);
-      ptx::mbar_wait(&bar_tfull[wg], t & 1);
-      ptx::tc_fence_after_sync();
-      uint32_t r0[32], r1[32], r2[32], r3[32];
-      ptx::tmem_ld32(taddr, r0);
-      ptx::tmem_ld32(taddr + 32, r1);
-      ptx::tmem_ld32(taddr + 64, r2);
-      ptx::tmem_ld32(taddr + 96, r3);
-      ptx::tmem_ld_wait();
+    int g = 0;
+    for (long long u = u_begin; u < u_end;) {
+      const int rb = (int)(u / sc.T), ct0 = (int)(u % sc.T);
+      const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
+      const int rblk0 = a.row_offset + rb * (2 * TBM) + wg * TBM;
+      const int gi = rblk0 + lrow;
+      // A_g may be rewritten: every MMA that read it has completed (this warpgroup saw the tfull of
+      // the previous segment's last tile)
+      load_rows_to_tmem(z, gi, a.n_total, tmem + lane_addr + TM_A + wg * (TD / 2));
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&bar_tempty[wg]);   // S_g is free again: the next MMA overlaps the work below
-      const bool masked = (col0 + BN > a.n_total) || (col0 < rblk0 + TBM && rblk0 < col0 + BN);
-      const int32_t* lab_s = lab_ring[slot];
-      const float* nrm_s = nrm_ring[UNI ? slot : 0];
-      if (masked) {
-        fwd_chunk<SIM, UNI, MINE, true>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-        fwd_chunk<SIM, UNI, MINE, true>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-        fwd_chunk<SIM, UNI, MINE, true>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-        fwd_chunk<SIM, UNI, MINE, true>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-      } else {
-        fwd_chunk<SIM, UNI, MINE, false>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-        fwd_chunk<SIM, UNI, MINE, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-        fwd_chunk<SIM, UNI, MINE, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-        fwd_chunk<SIM, UNI, MINE, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-      }
-    }
-    if (gi < a.row_offset + a.n_rows) {
-      const int64_t rec = (int64_t)split * a.rows_pad + (gi - a.row_offset);
-      float* out = a.part + rec * 8;
-      *reinterpret_cast<float4*>(out) = make_float4(st.sum_all, st.sum_pos_s, st.wsum, __int_as_float(st.npos));
-      *reinterpret_cast<float4*>(out + 4) = make_float4(st.sum_pos_e, __int_as_float(ms.cnt), 0.f, 0.f);
-      if (MINE) {
-        for (int e = 0; e < ms.cnt; ++e) {
-          a.topk_v[rec * K + e] = lv[e * LIST_STRIDE];
-          a.topk_i[rec * K + e] = li[e * LIST_STRIDE];
+      ptx::mbar_arrive(&bar_a);
+      const int lab_r = a.lab_pad[min(gi, a.n_pad - 1)];
+      const float nrm_r = UNI ? a.nrm_pad[min(gi, a.n_pad - 1)] : 0.f;
+      RowSums st;
+      st.sum_all = 0.f; st.sum_pos_s = 0.f; st.wsum = 0.f; st.npos = 0; st.sum_pos_e = 0.f;
+      MineState ms;
+      ms.thr = -INFINITY; ms.cnt = 0;
+      for (int t = 0; t < nt; ++t, ++g) {
+        const int slot = g % RING;
+        const int col0 = (ct0 + t) * BN;
+        ptx::mbar_wait(&bar_col[slot], (g / RING) & 1);
+        ptx::mbar_wait(&bar_tfull[wg], g & 1);
+        ptx::tc_fence_after_sync();
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        ptx::tmem_ld32(taddr, r0);
+        ptx::tmem_ld32(taddr + 32, r1);
+        ptx::tmem_ld32(taddr + 64, r2);
+        ptx::tmem_ld32(taddr + 96, r3);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(&bar_tempty[wg]);   // S_g is free again: the next MMA overlaps the work below
+        const bool masked = (col0 + BN > a.n_total) || (col0 < rblk0 + TBM && rblk0 < col0 + BN);
+        const int32_t* lab_s = lab_ring[slot];
+        const float* nrm_s = nrm_ring[UNI ? slot : 0];
+        if (masked) {
+          fwd_chunk<SIM, UNI, MINE, true>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+          fwd_chunk<SIM, UNI, MINE, true>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+          fwd_chunk<SIM, UNI, MINE, true>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+          fwd_chunk<SIM, UNI, MINE, true>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+        } else {
+          fwd_chunk<SIM, UNI, MINE, false>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+          fwd_chunk<SIM, UNI, MINE, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+          fwd_chunk<SIM, UNI, MINE, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+          fwd_chunk<SIM, UNI, MINE, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
         }
       }
+      if (gi < a.row_offset + a.n_rows) {
+        const int slot_out = (int)blockIdx.x - sched_cta_of(sc, (long long)rb * sc.T);
+        const int64_t rec = (int64_t)slot_out * a.rows_pad + (gi - a.row_offset);
+        float* out = a.part + rec * 8;
+        *reinterpret_cast<float4*>(out) = make_float4(st.sum_all, st.sum_pos_s, st.wsum, __int_as_float(st.npos));
+        *reinterpret_cast<float4*>(out + 4) = make_float4(st.sum_pos_e, __int_as_float(ms.cnt), 0.f, 0.f);
+        if (MINE) {
+          for (int e = 0; e < ms.cnt; ++e) {
+            a.topk_v[rec * K + e] = lv[e * LIST_STRIDE];
+            a.topk_i[rec * K + e] = li[e * LIST_STRIDE];
+          }
+        }
+      }
+      u += nt;
     }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<512>(tmem);
 }
-
 
 // merge the column splits into row statistics + loss partial sums
 __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishArgs f, float* __restrict__ row_stats) {
@@ -385,7 +419,12 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
   if (lr < a.n_rows) {
     float sum_all = 0.f, sum_pos_s = 0.f, wsum = 0.f, sum_pos_e = 0.f;
     int npos = 0;
-    for (int s = 0; s < a.splits; ++s) {
+    // partial records of this row: one per CTA whose unit range touches the row's 256-row block,
+    // in CTA order = ascending column order
+    const int rb = lr / (2 * TBM);
+    const int nslots = sched_cta_of(a.sched, (long long)rb * a.sched.T + a.sched.T - 1) -
+                       sched_cta_of(a.sched, (long long)rb * a.sched.T) + 1;
+    for (int s = 0; s < nslots; ++s) {
       const float* rec = a.part + ((int64_t)s * a.rows_pad + lr) * 8;
       const float4 v = *reinterpret_cast<const float4*>(rec);
       sum_all += v.x; sum_pos_s += v.y; wsum += v.z; npos += __float_as_int(v.w);
@@ -404,7 +443,7 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
       float mv[TC_KCAP];
       int mi[TC_KCAP];
       int cnt = 0;
-      for (int s = 0; s < a.splits; ++s) {
+      for (int s = 0; s < nslots; ++s) {
         const int64_t rec = (int64_t)s * a.rows_pad + lr;
         const int c = __float_as_int(a.part[rec * 8 + 5]);
         for (int e = 0; e < c; ++e) {
@@ -512,12 +551,13 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw
   }
 }
 
-// Backward: one CTA owns a 128-row block; Z_I lives in tensor memory (A operand of the
-// S MMAs), the two warpgroups take alternate 64-column tiles: pull S(t) into registers,
-// form H(t) and write it back as packed bf16 over the first 32 columns of the same S
-// buffer, from where it is the A operand of dZ += H Z_J (no shared-memory round trip).
-// Tensor-pipe order: S(0) S(1) dZ(0) S(2) dZ(1) ...; tcgen05.mma executes in issue order,
-// so S(t+2) cannot overwrite the buffer dZ(t) is still reading.
+// Backward: a persistent CTA walks a contiguous range of the flattened (128-row block, 64-column
+// tile) work list.  Per segment Z_I lives in tensor memory (A operand of the S MMAs); the two
+// warpgroups take alternate tiles: pull S(t) into registers, form H(t) and write it back as packed
+// bf16 over the first 32 columns of the same S buffer, from where it is the A operand of
+// dZ += H Z_J (no shared-memory round trip).  Tensor-pipe order within a segment:
+// S(0) S(1) dZ(0) S(2) dZ(1) ...; tcgen05.mma executes in issue order, so S(t+2) cannot overwrite
+// the buffer dZ(t) is still reading.  Barriers are indexed by a running tile counter.
 template <int SIM, bool UNI, bool MINE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapJ,
                                                              const __nv_bfloat16* __restrict__ z, TcBwdArgs a) {
@@ -530,7 +570,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sZJ = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_sfull[2], bar_hfull[2], bar_done,
-      bar_col[RING];
+      bar_dzfree, bar_col[RING];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) int32_t lab_ring[RING][BN];
   __shared__ __align__(16) float colA_ring[RING][BN], colB_ring[RING][BN];
@@ -539,15 +579,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   __shared__ __align__(16) int32_t thridx_ring[MINE ? RING : 1][BN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rb = blockIdx.x / a.splits, split = blockIdx.x % a.splits;
-  const int row0 = a.row_offset + rb * TBM;
-  const int ct_begin = (int)(((int64_t)a.col_tiles * split) / a.splits);
-  const int ct_end = (int)(((int64_t)a.col_tiles * (split + 1)) / a.splits);
-  const int ntiles = ct_end - ct_begin;
+  const TcSched sc = a.sched;
+  const long long u_begin = sched_begin(sc, blockIdx.x), u_end = sched_begin(sc, blockIdx.x + 1);
 
   if (tid == 0) {
     ptx::mbar_init(&bar_a, 128);
     ptx::mbar_init(&bar_done, 1);
+    ptx::mbar_init(&bar_dzfree, 256);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_hfull[b], 128); }
     for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
@@ -562,154 +600,181 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer (lane 0) + column-vector staging (all lanes) =====
-    for (int t = 0; t < ntiles; ++t) {
-      const int st = t % STAGES, use = t / STAGES, slot = t % RING;
-      const int col0 = (ct_begin + t) * BN;
-      // stage/slot st was last used by tile t-4; its release (dZ(t-4) complete) implies H(t-4) was formed
-      ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
-      if (ptx::elect_one()) {
-        ptx::mbar_expect_tx(&bar_full[st], TILEJ_BYTES);
-        for (int b = 0; b < NBOX; ++b)
-          ptx::tma_load_2d(sZJ + st * TILEJ_BYTES + b * BOXJ_BYTES, &tmapJ, &bar_full[st], 64 * b, col0);
-      }
-      if (lane < 16) {
-        *reinterpret_cast<int4*>(&lab_ring[slot][4 * lane]) =
-            __ldg(reinterpret_cast<const int4*>(a.lab_pad + col0 + 4 * lane));
-        *reinterpret_cast<float4*>(&colA_ring[slot][4 * lane]) =
-            __ldg(reinterpret_cast<const float4*>(a.colA + col0 + 4 * lane));
-      } else {
-        const int l = lane - 16;
-        *reinterpret_cast<float4*>(&colB_ring[slot][4 * l]) =
-            __ldg(reinterpret_cast<const float4*>(a.colB + col0 + 4 * l));
-        if (UNI)
-          *reinterpret_cast<float4*>(&nrm_ring[slot][4 * l]) =
-              __ldg(reinterpret_cast<const float4*>(a.nrm_pad + col0 + 4 * l));
-      }
-      if (MINE) {
+    int g = 0;
+    for (long long u = u_begin; u < u_end;) {
+      const int ct0 = (int)(u % sc.T);
+      const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
+      for (int t = 0; t < nt; ++t, ++g) {
+        const int st = g % STAGES, use = g / STAGES, slot = g % RING;
+        const int col0 = (ct0 + t) * BN;
+        // stage/slot st was last used by tile g-4; its release (dZ(g-4) complete) implies H(g-4) was formed
+        ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&bar_full[st], TILEJ_BYTES);
+          for (int b = 0; b < NBOX; ++b)
+            ptx::tma_load_2d(sZJ + st * TILEJ_BYTES + b * BOXJ_BYTES, &tmapJ, &bar_full[st], 64 * b, col0);
+        }
         if (lane < 16) {
-          *reinterpret_cast<float4*>(&colAm_ring[slot][4 * lane]) =
-              __ldg(reinterpret_cast<const float4*>(a.colAm + col0 + 4 * lane));
-          *reinterpret_cast<int4*>(&thridx_ring[slot][4 * lane]) =
-              __ldg(reinterpret_cast<const int4*>(a.colThrIdx + col0 + 4 * lane));
+          *reinterpret_cast<int4*>(&lab_ring[slot][4 * lane]) =
+              __ldg(reinterpret_cast<const int4*>(a.lab_pad + col0 + 4 * lane));
+          *reinterpret_cast<float4*>(&colA_ring[slot][4 * lane]) =
+              __ldg(reinterpret_cast<const float4*>(a.colA + col0 + 4 * lane));
         } else {
           const int l = lane - 16;
-          *reinterpret_cast<float4*>(&thr_ring[slot][4 * l]) =
-              __ldg(reinterpret_cast<const float4*>(a.colThr + col0 + 4 * l));
+          *reinterpret_cast<float4*>(&colB_ring[slot][4 * l]) =
+              __ldg(reinterpret_cast<const float4*>(a.colB + col0 + 4 * l));
+          if (UNI)
+            *reinterpret_cast<float4*>(&nrm_ring[slot][4 * l]) =
+                __ldg(reinterpret_cast<const float4*>(a.nrm_pad + col0 + 4 * l));
         }
+        if (MINE) {
+          if (lane < 16) {
+            *reinterpret_cast<float4*>(&colAm_ring[slot][4 * lane]) =
+                __ldg(reinterpret_cast<const float4*>(a.colAm + col0 + 4 * lane));
+            *reinterpret_cast<int4*>(&thridx_ring[slot][4 * lane]) =
+                __ldg(reinterpret_cast<const int4*>(a.colThrIdx + col0 + 4 * lane));
+          } else {
+            const int l = lane - 16;
+            *reinterpret_cast<float4*>(&thr_ring[slot][4 * l]) =
+                __ldg(reinterpret_cast<const float4*>(a.colThr + col0 + 4 * l));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar_col[slot]);
       }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar_col[slot]);
+      u += nt;
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: iteration t issues S(t) and then dZ(t-1) =====
+    // ===== MMA issuer: within a segment, iteration t issues S(t) and then dZ(t-1) =====
     if (ptx::elect_one()) {
       constexpr uint32_t idesc_s = ptx::idesc_bf16(128, BN, false, false);
       constexpr uint32_t idesc_dz = ptx::idesc_bf16(128, TD, false, true);
-      ptx::mbar_wait(&bar_a, 0);
-      for (int t = 0; t <= ntiles; ++t) {
-        if (t < ntiles) {
-          const int st = t % STAGES, use = t / STAGES, buf = t & 1;
-          ptx::mbar_wait(&bar_full[st], use & 1);
-          ptx::tc_fence_after_sync();
-          const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
+      int g0 = 0, seg = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        const int ct0 = (int)(u % sc.T);
+        const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
+        ptx::mbar_wait(&bar_a, seg & 1);              // Z_I of this segment is in tensor memory
+        ptx::mbar_wait(&bar_dzfree, (seg & 1) ^ 1);   // previous segment's dZ has been read out
+        for (int t = 0; t <= nt; ++t) {
+          if (t < nt) {
+            const int g = g0 + t;
+            const int st = g % STAGES, use = g / STAGES, buf = g & 1;
+            ptx::mbar_wait(&bar_full[st], use & 1);
+            ptx::tc_fence_after_sync();
+            const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
 #pragma unroll
-          for (int ks = 0; ks < TD / 16; ++ks) {
-            const uint32_t offb = (ks >> 2) * BOXJ_BYTES + (ks & 3) * 32;
-            ptx::mma_ts(tmem + TM_S + buf * BN, tmem + TM_A + 8 * ks, ptx::smem_desc_sw128(b0 + offb, 16, 1024),
-                        idesc_s, ks > 0);
+            for (int ks = 0; ks < TD / 16; ++ks) {
+              const uint32_t offb = (ks >> 2) * BOXJ_BYTES + (ks & 3) * 32;
+              ptx::mma_ts(tmem + TM_S + buf * BN, tmem + TM_A + 8 * ks, ptx::smem_desc_sw128(b0 + offb, 16, 1024),
+                          idesc_s, ks > 0);
+            }
+            ptx::mma_commit(&bar_sfull[buf]);
           }
-          ptx::mma_commit(&bar_sfull[buf]);
-        }
-        if (t >= 1) {
-          const int tt = t - 1;
-          const int st = tt % STAGES, buf = tt & 1, buse = tt >> 1;
-          ptx::mbar_wait(&bar_hfull[buf], buse & 1);
-          ptx::tc_fence_after_sync();
-          const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
+          if (t >= 1) {
+            const int g = g0 + t - 1;
+            const int st = g % STAGES, buf = g & 1, buse = g >> 1;
+            ptx::mbar_wait(&bar_hfull[buf], buse & 1);
+            ptx::tc_fence_after_sync();
+            const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < BN / 16; ++kk) {
-            ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + 8 * kk,
-                        ptx::smem_desc_sw128(b0 + kk * 16 * 128, BOXJ_BYTES, 1024), idesc_dz, (tt > 0 || kk > 0));
+            for (int kk = 0; kk < BN / 16; ++kk) {
+              ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + 8 * kk,
+                          ptx::smem_desc_sw128(b0 + kk * 16 * 128, BOXJ_BYTES, 1024), idesc_dz, (t > 1 || kk > 0));
+            }
+            ptx::mma_commit(&bar_empty[st]);
           }
-          ptx::mma_commit(&bar_empty[st]);
         }
+        ptx::mma_commit(&bar_done);
+        g0 += nt;
+        u += nt;
       }
-      ptx::mma_commit(&bar_done);
     }
   } else {
-    // ===== H warpgroups: warpgroup g takes tiles t = g, g+2, ... (S/H buffer g) =====
+    // ===== H warpgroups: warpgroup w takes the tiles with (running index & 1) == w (S/H buffer w) =====
     const int wg = (warp - 2) >> 2;
     const int lrow = 32 * (warp & 3) + lane;
-    const int gi = row0 + lrow;
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
-    if (wg == 0) {
-      load_rows_to_tmem(z, gi, a.n_total, tmem + lane_addr + TM_A);
-      ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&bar_a);
-    }
-    const int gic = min(gi, a.n_pad - 1);
-    const int lab_r = a.lab_pad[gic];
-    const float A_r = a.colA[gic], B_r = a.colB[gic];
-    const float nrm_r = UNI ? a.nrm_pad[gic] : 0.f;
     const float cu = UNI ? a.scalars[0] : 0.f;
-    RowMine rm;
-    rm.Am = MINE ? a.colAm[gic] : 0.f; rm.thr = MINE ? a.colThr[gic] : 0.f; rm.thr_idx = MINE ? a.colThrIdx[gic] : 0;
     const uint32_t sbuf = tmem + lane_addr + TM_S + wg * BN;
-    for (int t = wg; t < ntiles; t += 2) {
-      const int buse = t >> 1, slot = t % RING;
-      const int col0 = (ct_begin + t) * BN;
-      ptx::mbar_wait(&bar_col[slot], (t / RING) & 1);
-      ptx::mbar_wait(&bar_sfull[wg], buse & 1);
+    int g0 = 0, seg = 0;
+    for (long long u = u_begin; u < u_end; ++seg) {
+      const int rb = (int)(u / sc.T), ct0 = (int)(u % sc.T);
+      const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
+      const int row0 = a.row_offset + rb * TBM;
+      const int gi = row0 + lrow;
+      if (wg == 0) {
+        // the previous segment's MMAs (readers of Z_I) are complete: both warpgroups waited on bar_done
+        load_rows_to_tmem(z, gi, a.n_total, tmem + lane_addr + TM_A);
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(&bar_a);
+      }
+      const int gic = min(gi, a.n_pad - 1);
+      const int lab_r = a.lab_pad[gic];
+      const float A_r = a.colA[gic], B_r = a.colB[gic];
+      const float nrm_r = UNI ? a.nrm_pad[gic] : 0.f;
+      RowMine rm;
+      rm.Am = MINE ? a.colAm[gic] : 0.f; rm.thr = MINE ? a.colThr[gic] : 0.f; rm.thr_idx = MINE ? a.colThrIdx[gic] : 0;
+      for (int t = ((g0 & 1) == wg ? 0 : 1); t < nt; t += 2) {
+        const int g = g0 + t;
+        const int buse = g >> 1, slot = g % RING;
+        const int col0 = (ct0 + t) * BN;
+        ptx::mbar_wait(&bar_col[slot], (g / RING) & 1);
+        ptx::mbar_wait(&bar_sfull[wg], buse & 1);
+        ptx::tc_fence_after_sync();
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld32(sbuf, r0);
+        ptx::tmem_ld32(sbuf + 32, r1);
+        ptx::tmem_ld_wait();
+        uint32_t hw[32];
+        uint32_t (&h0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[0]);
+        uint32_t (&h1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[16]);
+        ColVecs cv0, cv1;
+        cv0.lab = lab_ring[slot]; cv0.A = colA_ring[slot]; cv0.B = colB_ring[slot]; cv0.nrm = nrm_ring[UNI ? slot : 0];
+        cv0.Am = colAm_ring[MINE ? slot : 0]; cv0.thr = thr_ring[MINE ? slot : 0]; cv0.thr_idx = thridx_ring[MINE ? slot : 0];
+        cv1.lab = cv0.lab + 32; cv1.A = cv0.A + 32; cv1.B = cv0.B + 32; cv1.nrm = cv0.nrm + 32;
+        cv1.Am = cv0.Am + 32; cv1.thr = cv0.thr + 32; cv1.thr_idx = cv0.thr_idx + 32;
+        const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
+        if (masked) {
+          bwd_chunk<SIM, UNI, MINE, true>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, rm, a);
+          bwd_chunk<SIM, UNI, MINE, true>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, rm, a);
+        } else {
+          bwd_chunk<SIM, UNI, MINE, false>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, rm, a);
+          bwd_chunk<SIM, UNI, MINE, false>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, rm, a);
+        }
+        ptx::tmem_st32(sbuf, hw);            // H(t): 64 bf16 = 32 packed columns over S(t)
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(&bar_hfull[wg]);
+      }
+      // ---- segment epilogue: dZ rows out of TMEM; warpgroup w writes columns 128w..128w+127 ----
+      ptx::mbar_wait(&bar_done, seg & 1);
       ptx::tc_fence_after_sync();
-      uint32_t r0[32], r1[32];
-      ptx::tmem_ld32(sbuf, r0);
-      ptx::tmem_ld32(sbuf + 32, r1);
-      ptx::tmem_ld_wait();
-      uint32_t hw[32];
-      uint32_t (&h0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[0]);
-      uint32_t (&h1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[16]);
-      ColVecs cv0, cv1;
-      cv0.lab = lab_ring[slot]; cv0.A = colA_ring[slot]; cv0.B = colB_ring[slot]; cv0.nrm = nrm_ring[UNI ? slot : 0];
-      cv0.Am = colAm_ring[MINE ? slot : 0]; cv0.thr = thr_ring[MINE ? slot : 0]; cv0.thr_idx = thridx_ring[MINE ? slot : 0];
-      cv1.lab = cv0.lab + 32; cv1.A = cv0.A + 32; cv1.B = cv0.B + 32; cv1.nrm = cv0.nrm + 32;
-      cv1.Am = cv0.Am + 32; cv1.thr = cv0.thr + 32; cv1.thr_idx = cv0.thr_idx + 32;
-      const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
-      if (masked) {
-        bwd_chunk<SIM, UNI, MINE, true>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, rm, a);
-        bwd_chunk<SIM, UNI, MINE, true>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, rm, a);
-      } else {
-        bwd_chunk<SIM, UNI, MINE, false>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, rm, a);
-        bwd_chunk<SIM, UNI, MINE, false>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, rm, a);
-      }
-      ptx::tmem_st32(sbuf, hw);            // H(t): 64 bf16 = 32 packed columns over S(t)
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&bar_hfull[wg]);
-    }
-    // ---- epilogue: dZ rows out of TMEM; warpgroup g writes columns 128g..128g+127 ----
-    ptx::mbar_wait(&bar_done, 0);
-    ptx::tc_fence_after_sync();
-    const bool row_ok = gi < a.row_offset + a.n_rows;
-    float* outp = a.dz_part + ((int64_t)split * a.rows_pad + (gi - a.row_offset)) * TD + 128 * wg;
+      const bool row_ok = gi < a.row_offset + a.n_rows;
+      const int slot_out = (int)blockIdx.x - sched_cta_of(sc, (long long)rb * sc.T);
+      float* outp = a.dz_part + ((int64_t)slot_out * a.rows_pad + (gi - a.row_offset)) * TD + 128 * wg;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld32(tmem + lane_addr + TM_DZ + 128 * wg + 32 * c, r);
-      ptx::tmem_ld_wait();
-      if (row_ok) {
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem + lane_addr + TM_DZ + 128 * wg + 32 * c, r);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(outp + 32 * c + 4 * q) =
-              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                          __uint_as_float(r[4 * q + 3]));
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(outp + 32 * c + 4 * q) =
+                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                            __uint_as_float(r[4 * q + 3]));
+        }
       }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&bar_dzfree);
+      g0 += nt;
+      u += nt;
     }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<512>(tmem);
 }
-
 
 // sum the column splits, add the uniformity diagonal term, scale by grad_out, convert
 template <typename TO>
@@ -721,7 +786,10 @@ __global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const _
   const int lr = (int)(idx4 / per_row), c4 = (int)(idx4 % per_row);
   if (lr >= a.n_rows) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < a.splits; ++s) {
+  const int rb = lr / TBM;
+  const int nslots = sched_cta_of(a.sched, (long long)rb * a.sched.T + a.sched.T - 1) -
+                     sched_cta_of(a.sched, (long long)rb * a.sched.T) + 1;
+  for (int s = 0; s < nslots; ++s) {
     const float4 v = *reinterpret_cast<const float4*>(a.dz_part + ((int64_t)s * a.rows_pad + lr) * TD + 4 * c4);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
@@ -750,24 +818,23 @@ int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-// Column splits per row block.  All CTAs are equal-sized, so the launch runs in
-// ceil(ctas / SMs) waves; pick the split count that maximises
-//   (wave balance) x (useful tiles / (useful tiles + per-CTA prologue/epilogue cost in tiles)).
-int choose_splits(int row_blocks, int col_tiles, int num_sms, const char* env_override, int overhead_tiles) {
-  int forced = env_int(env_override, 0);
-  if (forced > 0) return forced > col_tiles ? col_tiles : forced;
-  int best = 1;
-  double best_eff = 0.0;
-  const int max_s = col_tiles < 64 ? col_tiles : 64;
-  for (int sp = 1; sp <= max_s; ++sp) {
-    const double ctas = (double)row_blocks * sp;
-    const double waves = ceil(ctas / num_sms);
-    const double balance = ctas / (waves * num_sms);
-    const double tiles = (double)col_tiles / sp;
-    const double eff = balance * tiles / (tiles + overhead_tiles);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
+TcSched make_sched(int row_blocks, int col_tiles, int num_sms, const char* env_ctas) {
+  TcSched sc;
+  sc.T = col_tiles;
+  sc.U = (long long)row_blocks * col_tiles;
+  long long p = env_int(env_ctas, num_sms);
+  if (p > sc.U) p = sc.U;
+  if (p < 1) p = 1;
+  sc.P = (int)p;
+  return sc;
+}
+int sched_max_slots(const TcSched& sc, int row_blocks) {
+  int m = 1;
+  for (int rb = 0; rb < row_blocks; ++rb) {
+    int n = sched_cta_of(sc, (long long)rb * sc.T + sc.T - 1) - sched_cta_of(sc, (long long)rb * sc.T) + 1;
+    if (n > m) m = n;
   }
-  return best;
+  return m;
 }
 
 int g_num_sms = 0;
@@ -794,8 +861,10 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.fwd_row_blocks = (pl.row_blocks + 1) / 2;   // forward CTAs own two 128-row blocks
   pl.fwd_col_tiles = pl.n_pad / 128;
   pl.bwd_col_tiles = (p->n_total + 63) / 64;
-  pl.fwd_splits = choose_splits(pl.fwd_row_blocks, pl.fwd_col_tiles, num_sms(), "SUPCON_TC_FWD_SPLITS", env_int("SUPCON_TC_FWD_OVH", 5));
-  pl.bwd_splits = choose_splits(pl.row_blocks, pl.bwd_col_tiles, num_sms(), "SUPCON_TC_BWD_SPLITS", env_int("SUPCON_TC_BWD_OVH", 12));
+  pl.fwd_sched = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles, num_sms(), "SUPCON_TC_FWD_CTAS");
+  pl.bwd_sched = make_sched(pl.row_blocks, pl.bwd_col_tiles, num_sms(), "SUPCON_TC_BWD_CTAS");
+  pl.fwd_splits = sched_max_slots(pl.fwd_sched, pl.fwd_row_blocks);
+  pl.bwd_splits = sched_max_slots(pl.bwd_sched, pl.row_blocks);
   pl.merge_blocks = pl.rows_pad / 128;
   size_t off = 256;
   pl.off_block_partials = off; off += align_up((size_t)pl.merge_blocks * SUPCON_N_PARTIALS * sizeof(double), 256);
@@ -867,7 +936,7 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
   a.nrm_pad = reinterpret_cast<const float*>(ws + pl.off_nrm);
   a.part = reinterpret_cast<float*>(ws + pl.off_part);
   a.n_total = p->n_total; a.n_pad = pl.n_pad; a.row_offset = p->row_offset; a.n_rows = p->n_rows;
-  a.rows_pad = pl.rows_pad; a.splits = pl.fwd_splits; a.col_tiles = pl.fwd_col_tiles; a.topk = p->topk;
+  a.rows_pad = pl.rows_pad; a.sched = pl.fwd_sched; a.topk = p->topk;
   a.inv_tau = 1.0f / p->tau;
   a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
   const bool mine = p->alpha != 0.f && p->topk >= 1;
@@ -876,7 +945,7 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
   a.topk_v = reinterpret_cast<float*>(ws + pl.off_topk_v);
   a.topk_i = reinterpret_cast<int32_t*>(ws + pl.off_topk_i);
   const size_t smem = 3 * (size_t)NBOX * 128 * 128 + 1024;   // 3 tile stages, or 2 stages + 64 KB of top-K lists
-  const int ctas = pl.fwd_row_blocks * pl.fwd_splits;
+  const int ctas = pl.fwd_sched.P;
   const bool geo = p->similarity == SUPCON_GEODESIC;
   const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
   if (geo && uni) e = launch_fwd_m<SUPCON_GEODESIC, true>(mine, tm, zb, a, ctas, smem, stream);
@@ -945,11 +1014,11 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   a.colAm = pa.colAm; a.colThr = pa.colThr; a.colThrIdx = pa.colThrIdx;
   a.dz_part = reinterpret_cast<float*>(ws + pl.off_part);
   a.n_total = p->n_total; a.n_pad = pl.n_pad; a.row_offset = p->row_offset; a.n_rows = p->n_rows;
-  a.rows_pad = pl.rows_pad; a.splits = pl.bwd_splits; a.col_tiles = pl.bwd_col_tiles;
+  a.rows_pad = pl.rows_pad; a.sched = pl.bwd_sched;
   a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
   a.scalars = pa.scalars;
   const size_t smem = 4 * (size_t)NBOX * 64 * 128 + 1024;
-  const int ctas = pl.row_blocks * pl.bwd_splits;
+  const int ctas = pl.bwd_sched.P;
   const bool geo = p->similarity == SUPCON_GEODESIC;
   const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
   const bool mine = p->alpha != 0.f && p->topk >= 1;
