@@ -822,7 +822,10 @@ TcSched make_sched(int row_blocks, int col_tiles, int num_sms, const char* env_c
   TcSched sc;
   sc.T = col_tiles;
   sc.U = (long long)row_blocks * col_tiles;
-  long long p = env_int(env_ctas, num_sms);
+  // two CTAs' worth of work per SM: the hardware scheduler evens out SM-to-SM speed differences
+  // (measured: rank share of N/8 rows 0.714 -> 0.694 ms), as long as a CTA still gets >= 32 tiles
+  long long p = env_int(env_ctas, 0);
+  if (p <= 0) p = (sc.U / (2LL * num_sms) >= 32) ? 2LL * num_sms : num_sms;
   if (p > sc.U) p = sc.U;
   if (p < 1) p = 1;
   sc.P = (int)p;
