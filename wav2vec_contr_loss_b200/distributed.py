@@ -5,7 +5,8 @@ Rank r holds the embeddings/labels of its local batch = rows
 
   forward   all_gather(z) + all_gather(labels)          (one coalesced NCCL launch over NVLink)
             row-block forward kernel  -> row stats + 8 partial sums
-            all_reduce(partials) + all_gather(row stats, N x 32 B)   (one coalesced launch)
+            all_gather(partial sums) + all_gather(row stats, N x 32 B)   (one coalesced launch;
+            the partials are summed in rank order on every rank: deterministic)
             -> scalar loss (identical on every rank)
   backward  row-block backward kernel: dz_i = sum_j (G_ij + G_ji) z_j for the
             owned rows, recomputing the tiles.  Because the similarity matrix
@@ -75,10 +76,20 @@ def gather_inputs(z_local: torch.Tensor, labels_local: torch.Tensor, group=None)
 
 
 def exchange_stats(partials: torch.Tensor, stats: torch.Tensor, group=None):
-    """all-reduce of the 8 partial sums + all-gather of the row statistics in ONE collective launch."""
+    """Global partial sums + row statistics of every rank in ONE collective launch: the 8 fp64 partial
+    sums travel as 16 fp32 words beside the statistics (two all-gathers of the same dtype coalesce; an
+    all-reduce would not) and are summed on every rank in rank order, so the result is deterministic.
+    ``partials`` is overwritten with the global sums; returns stats_all."""
     world = dist.get_world_size(group)
     stats_all = torch.empty((world * stats.size(0),) + tuple(stats.shape[1:]), dtype=stats.dtype, device=stats.device)
-    with _coalesced(group, stats.device):
+    if partials.dtype == torch.float64 and stats.dtype == torch.float32:
+        p32 = partials.view(torch.float32)
+        p_all = torch.empty(world * p32.numel(), dtype=torch.float32, device=partials.device)
+        with _coalesced(group, stats.device):
+            dist.all_gather_into_tensor(p_all, p32, group=group)
+            dist.all_gather_into_tensor(stats_all, stats.contiguous(), group=group)
+        partials.copy_(p_all.view(torch.float64).view(world, -1).sum(dim=0))
+    else:   # generic fallback (CPU stand-in kernels in the gloo tests)
         dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
         dist.all_gather_into_tensor(stats_all, stats.contiguous(), group=group)
     return stats_all
