@@ -50,6 +50,13 @@ def parse():
     ap.add_argument("--cpu-sample-n", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: N fixed (BASELINE configs[3] as named); weak: per-GPU pair count fixed, "
+                         "N = batch-n * sqrt(gpus)")
+    ap.add_argument("--workload", default="loss", choices=["loss", "stage1"],
+                    help="loss: the SupCon hot path (default, BASELINE configs[3]); stage1: one Stage-1 training step "
+                         "around it (BASELINE configs[4]) reporting the loss's share of the step")
+    ap.add_argument("--stage1-batch", type=int, default=64)
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -185,8 +192,117 @@ def workload_config(args, extra=None):
     return cfg
 
 
+def run_stage1(args):
+    """BASELINE configs[4]: the caller's Stage-1 step (reference stage1_utils.py:110-132) around the loss, on a
+    random-init XLS-R-300M (no checkpoints offline) and synthetic 4 s / 16 kHz audio, batch 64 per GPU, frozen
+    encoder (CLI default finetune_encoder=0, stage1_config.py:30), compression head trained with AdamW.
+    Reports ms/step and the share of the step spent in the loss (forward + backward to z) for three losses:
+    this library, a vectorised torch restatement (cuBLAS + logsumexp: what a careful user would write), and the
+    per-anchor loop port of the reference's loss.py (the baseline leg: oracle/supcon_oracle.py)."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from transformers import Wav2Vec2Config, Wav2Vec2Model
+    from wav2vec_contr_loss_b200 import build as _build
+    _build.build()
+    from wav2vec_contr_loss_b200 import SupConBinaryLoss
+    from oracle import supcon_oracle as O
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    torch.manual_seed(1337)
+    cfg = Wav2Vec2Config(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
+                         feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True, conv_dim=(512,) * 7,
+                         conv_stride=(5, 2, 2, 2, 2, 2, 2), conv_kernel=(10, 3, 3, 3, 3, 2, 2),
+                         num_conv_pos_embeddings=128, num_conv_pos_embedding_groups=16, layerdrop=0.0)
+    encoder = Wav2Vec2Model(cfg).to(dev).eval()
+    for p_ in encoder.parameters():
+        p_.requires_grad = False
+
+    class LayerMeanHead(nn.Module):   # shape/ops of the reference's compression head (compression_module.py:35-67)
+        def __init__(self):
+            super().__init__()
+            self.drop, self.act, self.proj = nn.Dropout(0.1), nn.LeakyReLU(), nn.Linear(1024, 256)
+
+        def forward(self, hs):        # (B, K, F, T) -> (B, 256, T)
+            x = self.act(self.drop(hs.mean(dim=1)))
+            return self.proj(x.transpose(1, 2)).transpose(1, 2)
+
+    head = LayerMeanHead().to(dev).train()
+    opt = torch.optim.AdamW(head.parameters(), lr=1e-4)
+    B = args.stage1_batch
+    wave = torch.randn(B, 64000, device=dev)
+    labels = (torch.arange(B, device=dev) % 2).long()
+    tau, topk, alpha = args.tau, args.topk, args.alpha
+
+    def vectorised_loss(z, y):        # plain torch restatement of the full SupCon term (cosine, alpha = 0)
+        n = z.size(0)
+        lg = (z @ z.t()) / tau
+        eye = torch.eye(n, dtype=torch.bool, device=z.device)
+        lg = lg.masked_fill(eye, float("-inf"))
+        pos = (y.view(-1, 1) == y.view(1, -1)) & ~eye
+        lse = torch.logsumexp(lg, dim=1)
+        npos = pos.sum(1)
+        per = lse - (lg.masked_fill(~pos, 0.0).sum(1) / npos.clamp_min(1))
+        return per[npos > 0].mean()
+
+    ours = SupConBinaryLoss(temperature=tau, similarity=args.similarity, uniformity_weight=args.lambda_uni)
+    losses = {
+        "b200_kernel": lambda z, y: ours(z, y, topk_neg=topk, alpha=alpha),
+        "torch_vectorised": vectorised_loss,
+        "reference_port": lambda z, y: O.anchor_loop_loss(z, y, temperature=tau, similarity=args.similarity,
+                                                          uniformity_weight=args.lambda_uni, topk_neg=topk, alpha=alpha),
+    }
+
+    def embed():
+        with torch.no_grad():
+            out = encoder(wave, attention_mask=torch.ones_like(wave, dtype=torch.long), output_hidden_states=True)
+            hs = torch.stack(out.hidden_states, dim=0).transpose(0, 1).permute(0, 1, 3, 2).contiguous()
+        return F.normalize(head(hs).mean(dim=-1), p=2, dim=1)
+
+    def full_step(loss_fn):
+        z = embed()
+        loss = loss_fn(z, labels)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(head.parameters(), 5.0)
+        opt.step()
+        return loss.item()
+
+    def timed(fn, reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0) / reps
+
+    z_fixed = embed().detach()
+
+    def loss_only(loss_fn):
+        z = z_fixed.clone().requires_grad_(True)
+        loss_fn(z, labels).backward()
+
+    result = {"workload": "stage1_step (BASELINE configs[4])", "batch": B, "encoder": "random-init XLS-R-300M, frozen",
+              "audio": "synthetic 4 s @ 16 kHz", "similarity": args.similarity, "tau": tau, "alpha": alpha,
+              "encoder_params_M": round(sum(p_.numel() for p_ in encoder.parameters()) / 1e6, 1),
+              "step_ms": {}, "loss_fwd_bwd_ms": {}, "loss_share_of_step": {}, "loss_value": {}}
+    for name, fn in losses.items():
+        for _ in range(max(2, args.warmup)):
+            full_step(fn)
+        result["loss_value"][name] = full_step(fn)
+        result["step_ms"][name] = timed(lambda: full_step(fn), max(3, min(args.steps, 10)))
+        loss_only(fn)
+        result["loss_fwd_bwd_ms"][name] = timed(lambda: loss_only(fn), 20)
+        result["loss_share_of_step"][name] = result["loss_fwd_bwd_ms"][name] / result["step_ms"][name]
+    print(json.dumps(result), flush=True)
+
+
 def main():
     args = parse()
+    if args.workload == "stage1":
+        run_stage1(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
@@ -208,6 +324,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     tdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    if args.scaling == "weak" and world > 1:
+        # per-GPU work (N^2 / R pairs) held at the single-GPU workload's: N grows like sqrt(R)
+        unit = 256 * world
+        args.n = int(round(args.n * (world ** 0.5) / unit)) * unit
     n, d = args.n, args.d
     assert n % world == 0
     n_local = n // world
@@ -380,7 +500,7 @@ def main():
         line = {
             "metric": METRIC, "value": pairs / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args),
             "clocks": clocks,
