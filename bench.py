@@ -311,7 +311,7 @@ def main():
     from wav2vec_contr_loss_b200 import build as _build
     _build.build()
     from wav2vec_contr_loss_b200 import functional as Fn
-    from wav2vec_contr_loss_b200.distributed import exchange_stats, gather_inputs
+    from wav2vec_contr_loss_b200.distributed import _CudaKernels, exchange_stats, gather_and_forward, gather_inputs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -342,31 +342,28 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     launches = {"count": 0}
 
-    def step(z_loc, y_loc, timing=None):
+    def step(z_loc, y_loc):
         """fwd + bwd through the C-ABI wrappers; returns (loss, dz_local)."""
         if world > 1:
-            z_all, y_all = gather_inputs(z_loc, y_loc)
+            # all-gather overlapped with the forward over the rank's own columns (distributed.gather_and_forward)
+            z_all, y_all, prob, stats, partials = gather_and_forward(
+                z_loc, y_loc, lambda nt, dd, ro, nr: Fn.make_problem(nt, dd, Fn._dtype_id(z_loc), row_offset=ro,
+                                                                     n_rows=nr, **kw), None, _CudaKernels)
+            loss = None
         else:
             z_all, y_all = z_loc, y_loc
-        prob = Fn.make_problem(n, d, Fn._dtype_id(z_all), row_offset=rank * n_local, n_rows=n_local, **kw)
-        if timing:
-            timing[0].record()
-        stats, partials, loss = Fn.forward_rows(z_all, y_all, prob, want_loss=(world == 1))
-        if timing:
-            timing[1].record()
+            prob = Fn.make_problem(n, d, Fn._dtype_id(z_all), row_offset=0, n_rows=n, **kw)
+            stats, partials, loss = Fn.forward_rows(z_all, y_all, prob, want_loss=True)
         if world > 1:
             stats_all = exchange_stats(partials, stats)
             loss = Fn.finalize(prob, partials)
         else:
             stats_all = stats
-        if timing:
-            timing[2].record()
         dz = Fn.backward_rows(z_all, y_all, stats_all, partials, None, prob, out_dtype=tdtype)
-        if timing:
-            timing[3].record()
         # kernels of libsupcon_b200.so per step on the tensor path: prep_fwd, tc_fwd, merge, prep_bwd, tc_bwd,
-        # reduce (+ finalize when the loss comes from all-reduced partials)
-        launches["count"] += 6 + (1 if world > 1 else 0)
+        # reduce; with several ranks the forward runs in two phases (prep + tc_fwd twice) and a finalize kernel
+        # turns the exchanged partial sums into the loss
+        launches["count"] += 6 + (3 if world > 1 else 0)
         return loss, dz
 
     class Stepper:

@@ -102,6 +102,20 @@ int supcon_forward_rows(const supcon_problem_t* p, const void* z_all, const int3
                         float* row_stats, double* partials, float* loss_out, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* Two-phase form of supcon_forward_rows for ranks that overlap the all-gather of z with compute:
+ *   _local  sweeps only the columns this rank owns (rows [row_offset, row_offset + n_rows) of z_all and
+ *           labels_all must be valid; nothing from other ranks is read) and leaves partial records in
+ *           the workspace;
+ *   _remote sweeps all other columns (the whole z_all / labels_all must be valid), merges both phases and
+ *           writes row_stats / partials exactly as supcon_forward_rows would.
+ * Both calls take the SAME workspace.  When the problem is not eligible (exact path, unaligned row block)
+ * _local does nothing and _remote runs the whole forward. */
+int supcon_forward_rows_local(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int supcon_forward_rows_remote(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                               float* row_stats, double* partials, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
 /* Scalar loss from globally summed partials (alpha blend, empty-set fall-backs,
  * uniformity term): loss.py:137-153. */
 int supcon_finalize(const supcon_problem_t* p, const double* partials_global, float* loss_out,

@@ -378,3 +378,22 @@ def test_tensor_core_path_mining(cuda_device, n, kind, classes, sim, tau, lam, a
     assert float((st[:, 1].double() - ref["stats"]["lse_m"]).abs().max()) < 1e-4
     dz = Fn.backward_rows(z, yy, stats, partials, None, prob, out_dtype=torch.float32)
     assert G.rel_err(dz.cpu(), ref["dz"]) < TOL_BF16
+
+
+@pytest.mark.parametrize("sim,lam,alpha,k", [("cosine", 0.0, 0.0, 15), ("geodesic", 0.05, 0.5, 7)])
+def test_two_phase_forward_equals_single_phase(cuda_device, sim, lam, alpha, k):
+    """supcon_forward_rows_local + _remote (own columns first, then the rest) == supcon_forward_rows."""
+    from wav2vec_contr_loss_b200 import functional as Fn
+    n = 2048
+    x, y = O.make_inputs(n, 256, "ties", classes=3)
+    z = Fn.canonical_z(F.normalize(x, dim=1).to(torch.bfloat16).to(cuda_device))
+    yy = Fn.canonical_labels(y.to(cuda_device), n)
+    for row_offset, n_rows in ((512, 768), (0, 256), (1792, 256)):
+        prob = Fn.make_problem(n, 256, 1, tau=0.07, similarity=Fn.similarity_id(sim), lambda_uni=lam, topk=k, alpha=alpha,
+                               flags=2, row_offset=row_offset, n_rows=n_rows)
+        s1, p1, _ = Fn.forward_rows(z, yy, prob, want_loss=False)
+        ws = Fn.forward_rows_local(z, yy, prob)
+        s2, p2 = Fn.forward_rows_remote(z, yy, prob, ws)
+        assert torch.equal(s1.view(torch.int32)[:, [2, 3, 5]], s2.view(torch.int32)[:, [2, 3, 5]])   # counts, threshold idx
+        assert torch.allclose(s1[:, [0, 1, 6, 7]], s2[:, [0, 1, 6, 7]], rtol=1e-5, atol=1e-6)       # sums: order differs
+        assert torch.allclose(p1, p2, rtol=1e-6)

@@ -21,7 +21,8 @@ ST_LSE, ST_LSE_M, ST_NPOS, ST_NNEG, ST_THR_VAL, ST_THR_IDX, ST_WSUM, ST_POS_MEAN
 EXPORTS = (
     "supcon_abi_version", "supcon_last_error", "supcon_workspace_bytes", "supcon_forward_rows",
     "supcon_finalize", "supcon_backward_rows", "supcon_loss_and_grad", "supcon_normalize_forward",
-    "supcon_normalize_backward", "supcon_topk_indices", "supcon_debug_tc_tile",
+    "supcon_normalize_backward", "supcon_topk_indices", "supcon_debug_tc_tile", "supcon_forward_rows_local",
+    "supcon_forward_rows_remote",
 )
 
 
@@ -61,6 +62,10 @@ def load():
     lib.supcon_forward_rows.restype = c_int32
     lib.supcon_forward_rows.argtypes = [P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_size_t, c_void_p]
+    lib.supcon_forward_rows_local.restype = c_int32
+    lib.supcon_forward_rows_local.argtypes = [P, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.supcon_forward_rows_remote.restype = c_int32
+    lib.supcon_forward_rows_remote.argtypes = [P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.supcon_finalize.restype = c_int32
     lib.supcon_finalize.argtypes = [P, c_void_p, c_void_p, c_void_p]
     lib.supcon_backward_rows.restype = c_int32

@@ -200,6 +200,37 @@ int supcon_forward_rows(const supcon_problem_t* p, const void* z_all, const int3
   return 0;
 }
 
+int supcon_forward_rows_local(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!z_all || !labels_all || !workspace) return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_forward_rows_local");
+  if (workspace_bytes < workspace_need(p))
+    return fail(SUPCON_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, workspace_need(p));
+  if (!(use_tc(p, false) && tc_two_phase(p))) return 0;   // nothing to pre-compute: the second call does everything
+  const char* err = "";
+  int rc = tc_forward(p, z_all, labels_all, nullptr, nullptr, nullptr, workspace, reinterpret_cast<cudaStream_t>(stream),
+                      &err, 1);
+  if (rc) return fail(rc, "tc_forward(local columns): %s", err);
+  return 0;
+}
+
+int supcon_forward_rows_remote(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                               float* row_stats, double* partials, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!(use_tc(p, false) && tc_two_phase(p)))
+    return supcon_forward_rows(p, z_all, labels_all, row_stats, partials, nullptr, workspace, workspace_bytes, stream);
+  if (!z_all || !labels_all || !row_stats || !partials || !workspace)
+    return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_forward_rows_remote");
+  if (workspace_bytes < workspace_need(p))
+    return fail(SUPCON_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, workspace_need(p));
+  const char* err = "";
+  int rc = tc_forward(p, z_all, labels_all, row_stats, partials, nullptr, workspace,
+                      reinterpret_cast<cudaStream_t>(stream), &err, 2);
+  if (rc) return fail(rc, "tc_forward(remote columns): %s", err);
+  return 0;
+}
+
 int supcon_finalize(const supcon_problem_t* p, const double* partials_global, float* loss_out,
                     void* stream) {
   if (int rc = validate(p)) return rc;

@@ -38,6 +38,9 @@ struct TcSched {   // flattened (row block, column tile) work list cut into P co
 };
 struct TcPlan {
   TcSched fwd_sched, bwd_sched;
+  TcSched fwd_sched_local, fwd_sched_remote;   // two-phase forward (own columns first, then the others)
+  bool two_phase;
+  int local_ct0, local_cts, slots_local;
   int n_pad, rows_pad, row_blocks, fwd_row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_splits, bwd_splits, merge_blocks;
   size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
       off_scalars, off_topk_v, off_topk_i, off_part, total_bytes;
@@ -49,6 +52,8 @@ struct TcFwdArgs {
   float* topk_v;     // [splits][rows_pad][kcap]  per-split hard-negative candidates (mining)
   int32_t* topk_i;
   TcSched sched;
+  TcSched sched_b;   // merge only: second pass of the two-phase forward (P == 0: none)
+  int ct_base, ex_lo, ex_len, slot_base, slot_base_b;
   int n_total, n_pad, row_offset, n_rows, rows_pad, topk, mine, kcap;
   float inv_tau, c1, c0, ut2;
 };
@@ -76,8 +81,10 @@ struct TcBwdArgs {
 };
 TcPlan tc_plan(const supcon_problem_t* p);
 bool tc_supported(const supcon_problem_t* p);
+bool tc_two_phase(const supcon_problem_t* p);
 int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, float* row_stats,
-               double* partials, float* loss_out, void* workspace, cudaStream_t stream, const char** err);
+               double* partials, float* loss_out, void* workspace, cudaStream_t stream, const char** err,
+               int phase = 0);
 int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, const float* stats_all,
                 const double* partials_global, const float* grad_out, void* dz_out, int dz_dtype, void* workspace,
                 cudaStream_t stream, const char** err);

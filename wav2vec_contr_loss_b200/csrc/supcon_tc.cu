@@ -79,8 +79,10 @@ __device__ __forceinline__ float geodesic_slope_fast(float c) {
 // ---------------------------------------------------------------------------
 __global__ void tc_prep_fwd_kernel(const __nv_bfloat16* __restrict__ z, const int32_t* __restrict__ labels, int n,
                                    int n_pad, int d, int32_t* __restrict__ lab_pad, float* __restrict__ nrm_pad,
-                                   int want_norms) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+                                   int want_norms, int j_lo = 0, int ex_lo = 0x7fffffff, int ex_len = 0) {
+  // one warp per column j of [j_lo, n_pad), skipping the window [ex_lo, ex_lo + ex_len)
+  int warp = j_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= ex_lo) warp += ex_len;
   if (warp >= n_pad) return;
   float s = 0.f;
   if (warp < n && want_norms) {
@@ -215,6 +217,12 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
   }
 }
 
+// logical column tile of this launch -> physical tile: a launch covers [ct_base, ...) minus an excluded window
+// (the two-phase multi-GPU forward first sweeps the rank's own columns, then everything else)
+__device__ __forceinline__ int fwd_col_tile(const TcFwdArgs& a, int ct) {
+  return a.ct_base + ct + (ct >= a.ex_lo ? a.ex_len : 0);
+}
+
 // Z rows -> tensor memory as the A operand of tcgen05.mma (kind::f16, A from TMEM):
 // lane = row, 32-bit column m holds the bf16 pair (z[2m], z[2m+1]).
 __device__ __forceinline__ void load_rows_to_tmem(const __nv_bfloat16* __restrict__ z, int gi, int n_total,
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
       const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
       for (int t = 0; t < nt; ++t, ++g) {
         const int st = g % STAGES, use = g / STAGES, slot = g % RING;
-        const int col0 = (ct0 + t) * BN;
+        const int col0 = fwd_col_tile(a, ct0 + t) * BN;
         ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&bar_full[st], TILE_BYTES);
@@ -363,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
       ms.thr = -INFINITY; ms.cnt = 0;
       for (int t = 0; t < nt; ++t, ++g) {
         const int slot = g % RING;
-        const int col0 = (ct0 + t) * BN;
+        const int col0 = fwd_col_tile(a, ct0 + t) * BN;
         ptx::mbar_wait(&bar_col[slot], (g / RING) & 1);
         ptx::mbar_wait(&bar_tfull[wg], g & 1);
         ptx::tc_fence_after_sync();
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
         }
       }
       if (gi < a.row_offset + a.n_rows) {
-        const int slot_out = (int)blockIdx.x - sched_cta_of(sc, (long long)rb * sc.T);
+        const int slot_out = a.slot_base + (int)blockIdx.x - sched_cta_of(sc, (long long)rb * sc.T);
         const int64_t rec = (int64_t)slot_out * a.rows_pad + (gi - a.row_offset);
         float* out = a.part + rec * 8;
         *reinterpret_cast<float4*>(out) = make_float4(st.sum_all, st.sum_pos_s, st.wsum, __int_as_float(st.npos));
@@ -422,14 +430,22 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
     // partial records of this row: one per CTA whose unit range touches the row's 256-row block,
     // in CTA order = ascending column order
     const int rb = lr / (2 * TBM);
-    const int nslots = sched_cta_of(a.sched, (long long)rb * a.sched.T + a.sched.T - 1) -
-                       sched_cta_of(a.sched, (long long)rb * a.sched.T) + 1;
-    for (int s = 0; s < nslots; ++s) {
-      const float* rec = a.part + ((int64_t)s * a.rows_pad + lr) * 8;
-      const float4 v = *reinterpret_cast<const float4*>(rec);
-      sum_all += v.x; sum_pos_s += v.y; wsum += v.z; npos += __float_as_int(v.w);
-      sum_pos_e += rec[4];
-    }
+    // slot list of this row: pass A (a.sched, slots from a.slot_base) and, in the two-phase forward, pass B
+    int slot_lo[2], slot_n[2];
+    slot_lo[0] = a.slot_base;
+    slot_n[0] = sched_cta_of(a.sched, (long long)rb * a.sched.T + a.sched.T - 1) -
+                sched_cta_of(a.sched, (long long)rb * a.sched.T) + 1;
+    slot_lo[1] = a.slot_base_b;
+    slot_n[1] = a.sched_b.P > 0 ? sched_cta_of(a.sched_b, (long long)rb * a.sched_b.T + a.sched_b.T - 1) -
+                                      sched_cta_of(a.sched_b, (long long)rb * a.sched_b.T) + 1
+                                : 0;
+    for (int ps = 0; ps < 2; ++ps)
+      for (int s = slot_lo[ps]; s < slot_lo[ps] + slot_n[ps]; ++s) {
+        const float* rec = a.part + ((int64_t)s * a.rows_pad + lr) * 8;
+        const float4 v = *reinterpret_cast<const float4*>(rec);
+        sum_all += v.x; sum_pos_s += v.y; wsum += v.z; npos += __float_as_int(v.w);
+        sum_pos_e += rec[4];
+      }
     const int nneg = a.n_total - 1 - npos;
     const float lse = logf(sum_all) + a.inv_tau;   // fixed maximum 1/tau folded back in
     const float pos_mean = npos > 0 ? (sum_pos_s * a.inv_tau) / (float)npos : 0.f;
@@ -437,26 +453,29 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
     float thr_val = a.topk >= 1 ? -INFINITY : INFINITY;
     int thr_idx = a.topk >= 1 ? SUPCON_INT_MAX : -1;
     if (a.mine && nneg > a.topk) {
-      // merge the per-split top-K lists (splits cover ascending column ranges, each list is sorted by
-      // (value desc, index asc)): insertion with a strict compare keeps that order globally
+      // merge the per-segment top-K lists, each sorted by (value desc, index asc); the full (value, index)
+      // comparison makes the result independent of the order in which the segments are visited
       const int K = a.kcap;
       float mv[TC_KCAP];
       int mi[TC_KCAP];
       int cnt = 0;
-      for (int s = 0; s < nslots; ++s) {
-        const int64_t rec = (int64_t)s * a.rows_pad + lr;
-        const int c = __float_as_int(a.part[rec * 8 + 5]);
-        for (int e = 0; e < c; ++e) {
-          const float v = a.topk_v[rec * K + e];
-          const int ix = a.topk_i[rec * K + e];
-          int p;
-          if (cnt < K) p = cnt++;
-          else if (v > mv[K - 1]) p = K - 1;
-          else break;   // this list is sorted: nothing further down can enter
-          while (p > 0 && mv[p - 1] < v) { mv[p] = mv[p - 1]; mi[p] = mi[p - 1]; --p; }
-          mv[p] = v; mi[p] = ix;
+      for (int ps = 0; ps < 2; ++ps)
+        for (int s = slot_lo[ps]; s < slot_lo[ps] + slot_n[ps]; ++s) {
+          const int64_t rec = (int64_t)s * a.rows_pad + lr;
+          const int c = __float_as_int(a.part[rec * 8 + 5]);
+          for (int e = 0; e < c; ++e) {
+            const float v = a.topk_v[rec * K + e];
+            const int ix = a.topk_i[rec * K + e];
+            int p;
+            if (cnt < K) p = cnt++;
+            else if (v > mv[K - 1] || (v == mv[K - 1] && ix < mi[K - 1])) p = K - 1;
+            else break;   // this list is sorted: nothing further down can enter
+            while (p > 0 && (mv[p - 1] < v || (mv[p - 1] == v && mi[p - 1] > ix))) {
+              mv[p] = mv[p - 1]; mi[p] = mi[p - 1]; --p;
+            }
+            mv[p] = v; mi[p] = ix;
+          }
         }
-      }
       float sum_top = 0.f;
       for (int e = 0; e < K; ++e) sum_top += ex2f(fmaf(mv[e], a.c1, a.c0));
       lse_m = logf(sum_pos_e + sum_top) + a.inv_tau;
@@ -868,6 +887,17 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.bwd_sched = make_sched(pl.row_blocks, pl.bwd_col_tiles, num_sms(), "SUPCON_TC_BWD_CTAS");
   pl.fwd_splits = sched_max_slots(pl.fwd_sched, pl.fwd_row_blocks);
   pl.bwd_splits = sched_max_slots(pl.bwd_sched, pl.row_blocks);
+  // two-phase forward (multi-GPU overlap): phase 1 sweeps the rank's own columns, phase 2 the others
+  pl.two_phase = (p->n_rows < p->n_total) && (p->row_offset % 128 == 0) && (p->n_rows % 128 == 0);
+  pl.local_ct0 = p->row_offset / 128;
+  pl.local_cts = p->n_rows / 128;
+  if (pl.two_phase) {
+    pl.fwd_sched_local = make_sched(pl.fwd_row_blocks, pl.local_cts, num_sms(), "SUPCON_TC_FWD_CTAS");
+    pl.fwd_sched_remote = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles - pl.local_cts, num_sms(), "SUPCON_TC_FWD_CTAS");
+    pl.slots_local = sched_max_slots(pl.fwd_sched_local, pl.fwd_row_blocks);
+    int both = pl.slots_local + sched_max_slots(pl.fwd_sched_remote, pl.fwd_row_blocks);
+    if (both > pl.fwd_splits) pl.fwd_splits = both;
+  }
   pl.merge_blocks = pl.rows_pad / 128;
   size_t off = 256;
   pl.off_block_partials = off; off += align_up((size_t)pl.merge_blocks * SUPCON_N_PARTIALS * sizeof(double), 256);
@@ -914,8 +944,12 @@ static cudaError_t launch_fwd_m(bool mine, const CUtensorMap& tm, const __nv_bfl
   return mine ? launch_fwd<SIM, UNI, true>(tm, z, a, ctas, smem, st) : launch_fwd<SIM, UNI, false>(tm, z, a, ctas, smem, st);
 }
 
+bool tc_two_phase(const supcon_problem_t* p) { return tc_supported(p) && tc_plan(p).two_phase; }
+
+// phase: 0 = whole forward; 1 = only the columns this rank owns (partial records, needs nothing from other
+// ranks); 2 = all other columns + merge.  Phases 1 and 2 must use the same workspace.
 int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, float* row_stats,
-               double* partials, float* loss_out, void* workspace, cudaStream_t stream, const char** err) {
+               double* partials, float* loss_out, void* workspace, cudaStream_t stream, const char** err, int phase) {
   const TcPlan pl = tc_plan(p);
   char* ws = reinterpret_cast<char*>(workspace);
   CUtensorMap tm;
@@ -923,23 +957,36 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
     *err = "cuTensorMapEncodeTiled failed (z must be 16-byte aligned)";
     return SUPCON_E_INVALID;
   }
-  cudaError_t e = cudaMemsetAsync(workspace, 0, 256, stream);
-  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  cudaError_t e = cudaSuccess;
+  if (phase != 2) {
+    e = cudaMemsetAsync(workspace, 0, 256, stream);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  }
   const bool uni = p->lambda_uni > 0.f;
   {
+    // padded labels / squared norms of the columns this phase sweeps
+    int j_lo = 0, ex_lo = 0x7fffffff, ex_len = 0, count = pl.n_pad;
+    if (phase == 1) { j_lo = pl.local_ct0 * 128; count = pl.local_cts * 128; ex_lo = j_lo + count; ex_len = pl.n_pad; }
+    if (phase == 2) { ex_lo = pl.local_ct0 * 128; ex_len = pl.local_cts * 128; count = pl.n_pad - ex_len; }
     int threads = 256, warps_per_block = threads / 32;
-    int blocks = (pl.n_pad + warps_per_block - 1) / warps_per_block;
-    tc_prep_fwd_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all,
-                                                       p->n_total, pl.n_pad, p->d,
-                                                       reinterpret_cast<int32_t*>(ws + pl.off_lab),
-                                                       reinterpret_cast<float*>(ws + pl.off_nrm), uni ? 1 : 0);
+    int blocks = (count + warps_per_block - 1) / warps_per_block;
+    if (blocks > 0)
+      tc_prep_fwd_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all,
+                                                         p->n_total, pl.n_pad, p->d,
+                                                         reinterpret_cast<int32_t*>(ws + pl.off_lab),
+                                                         reinterpret_cast<float*>(ws + pl.off_nrm), uni ? 1 : 0, j_lo,
+                                                         ex_lo, ex_len);
   }
   TcFwdArgs a;
+  a.ct_base = 0; a.ex_lo = 0x7fffffff; a.ex_len = 0; a.slot_base = 0;
+  a.sched_b.P = 0; a.sched_b.T = 1; a.sched_b.U = 1; a.slot_base_b = 0;
   a.lab_pad = reinterpret_cast<const int32_t*>(ws + pl.off_lab);
   a.nrm_pad = reinterpret_cast<const float*>(ws + pl.off_nrm);
   a.part = reinterpret_cast<float*>(ws + pl.off_part);
   a.n_total = p->n_total; a.n_pad = pl.n_pad; a.row_offset = p->row_offset; a.n_rows = p->n_rows;
   a.rows_pad = pl.rows_pad; a.sched = pl.fwd_sched; a.topk = p->topk;
+  if (phase == 1) { a.sched = pl.fwd_sched_local; a.ct_base = pl.local_ct0; }
+  if (phase == 2) { a.sched = pl.fwd_sched_remote; a.ex_lo = pl.local_ct0; a.ex_len = pl.local_cts; a.slot_base = pl.slots_local; }
   a.inv_tau = 1.0f / p->tau;
   a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
   const bool mine = p->alpha != 0.f && p->topk >= 1;
@@ -948,7 +995,7 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
   a.topk_v = reinterpret_cast<float*>(ws + pl.off_topk_v);
   a.topk_i = reinterpret_cast<int32_t*>(ws + pl.off_topk_i);
   const size_t smem = 3 * (size_t)NBOX * 128 * 128 + 1024;   // 3 tile stages, or 2 stages + 64 KB of top-K lists
-  const int ctas = pl.fwd_sched.P;
+  const int ctas = a.sched.P;
   const bool geo = p->similarity == SUPCON_GEODESIC;
   const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
   if (geo && uni) e = launch_fwd_m<SUPCON_GEODESIC, true>(mine, tm, zb, a, ctas, smem, stream);
@@ -956,6 +1003,11 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
   else if (uni) e = launch_fwd_m<SUPCON_COSINE, true>(mine, tm, zb, a, ctas, smem, stream);
   else e = launch_fwd_m<SUPCON_COSINE, false>(mine, tm, zb, a, ctas, smem, stream);
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  if (phase == 1) return 0;   // partial records only; phase 2 merges
+  if (phase == 2) {           // merge sums the local-column records (pass A) and the remote ones (pass B)
+    a.sched_b = a.sched; a.slot_base_b = a.slot_base;
+    a.sched = pl.fwd_sched_local; a.slot_base = 0;
+  }
   FinishArgs f{reinterpret_cast<double*>(ws + pl.off_block_partials), reinterpret_cast<unsigned*>(ws), partials,
                loss_out, p->n_total, p->tau, p->alpha, p->lambda_uni, p->uni_t};
   tc_fwd_merge_kernel<<<pl.merge_blocks, 128, 0, stream>>>(a, f, row_stats);

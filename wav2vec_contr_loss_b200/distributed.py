@@ -46,6 +46,54 @@ class _CudaKernels:
     def backward_rows(z_all, labels_all, stats_all, partials, grad_out, prob, out_dtype):
         return Fn.backward_rows(z_all, labels_all, stats_all, partials, grad_out, prob, out_dtype=out_dtype)
 
+    # two-phase forward: own columns while the all-gather is in flight, then the rest
+    forward_rows_local = staticmethod(Fn.forward_rows_local)
+    forward_rows_remote = staticmethod(Fn.forward_rows_remote)
+
+
+_COMM_STREAMS = {}
+
+
+def _comm_stream(device) -> "torch.cuda.Stream":
+    key = (device.type, device.index)
+    if key not in _COMM_STREAMS:
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COMM_STREAMS[key]
+
+
+def gather_and_forward(z_local, labels_local, make_prob, group, kernels):
+    """all-gather(z, labels) overlapped with the forward over this rank's own columns.
+
+    The local block is copied into place first and the all-gather runs in place on a side stream, so the
+    phase-1 kernels (which read only that block) race with nothing.  Returns (z_all, labels_all, prob,
+    row_stats, partials)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_local, d = z_local.shape
+    dev = z_local.device
+    prob = make_prob(n_local * world, d, rank * n_local, n_local)
+    two_phase = dev.type == "cuda" and hasattr(kernels, "forward_rows_local")
+    if not two_phase:
+        z_all, labels_all = gather_inputs(z_local, labels_local, group)
+        stats, partials = kernels.forward_rows(z_all, labels_all, prob)
+        return z_all, labels_all, prob, stats, partials
+    z_all = torch.empty((world * n_local, d), dtype=z_local.dtype, device=dev)
+    y_all = torch.empty(world * n_local, dtype=labels_local.dtype, device=dev)
+    zb, yb = z_all[rank * n_local:(rank + 1) * n_local], y_all[rank * n_local:(rank + 1) * n_local]
+    zb.copy_(z_local)
+    yb.copy_(labels_local)
+    cur, comm = torch.cuda.current_stream(dev), _comm_stream(dev)
+    comm.wait_stream(cur)
+    with torch.cuda.stream(comm):
+        with _coalesced(group, dev):
+            dist.all_gather_into_tensor(z_all, zb, group=group)
+            dist.all_gather_into_tensor(y_all, yb, group=group)
+    z_all.record_stream(comm)
+    y_all.record_stream(comm)
+    ws = kernels.forward_rows_local(z_all, y_all, prob)      # runs while the all-gather is in flight
+    cur.wait_stream(comm)
+    stats, partials = kernels.forward_rows_remote(z_all, y_all, prob, ws)
+    return z_all, y_all, prob, stats, partials
+
 
 def _all_gather_rows(x: torch.Tensor, group) -> torch.Tensor:
     world = dist.get_world_size(group)
@@ -100,11 +148,11 @@ class _ShardedSupCon(torch.autograd.Function):
     def forward(ctx, z_local, labels_local, cfg, group, kernels):
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         zc = Fn.canonical_z(z_local.detach())
-        n_local, d = zc.shape
-        z_all, labels_all = gather_inputs(zc, labels_local, group)
-        prob = Fn.make_problem(n_local * world, d, Fn._dtype_id(zc), row_offset=rank * n_local, n_rows=n_local,
-                               **cfg)
-        stats, partials = kernels.forward_rows(z_all, labels_all, prob)
+
+        def make_prob(n_total, d, row_offset, n_rows):
+            return Fn.make_problem(n_total, d, Fn._dtype_id(zc), row_offset=row_offset, n_rows=n_rows, **cfg)
+
+        z_all, labels_all, prob, stats, partials = gather_and_forward(zc, labels_local, make_prob, group, kernels)
         if ctx.needs_input_grad[0]:
             stats_all = exchange_stats(partials, stats, group)
         else:

@@ -123,6 +123,33 @@ def loss_and_grad(z: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Problem
 SMALL_BATCH_MAX = 160   # supcon_small.cu: N <= 8 CTAs x 20 rows
 
 
+def forward_rows_local(z_all, labels_i32, prob: _cabi.Problem) -> torch.Tensor:
+    """Phase 1 of the two-phase row-block forward: sweep this rank's own columns.  Only rows
+    [row_offset, row_offset + n_rows) of z_all / labels need to be valid.  Returns the workspace that
+    forward_rows_remote must be given."""
+    _require_cuda(z_all, "z")
+    lib = _cabi.load()
+    dev = z_all.device
+    with torch.cuda.device(dev):
+        ws = workspace_for(prob, dev)
+        _cabi.check(lib.supcon_forward_rows_local(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(ws), ws.numel(),
+                                                  _stream(dev)), "supcon_forward_rows_local")
+    return ws
+
+
+def forward_rows_remote(z_all, labels_i32, prob: _cabi.Problem, ws: torch.Tensor):
+    """Phase 2: all other columns + merge. Returns (row_stats, partials) like forward_rows."""
+    lib = _cabi.load()
+    dev = z_all.device
+    with torch.cuda.device(dev):
+        stats = torch.empty((prob.n_rows, _cabi.STATS_STRIDE), dtype=torch.float32, device=dev)
+        partials = torch.empty(_cabi.N_PARTIALS, dtype=torch.float64, device=dev)
+        _cabi.check(lib.supcon_forward_rows_remote(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(stats),
+                                                   _p(partials), _p(ws), ws.numel(), _stream(dev)),
+                    "supcon_forward_rows_remote")
+    return stats, partials
+
+
 def finalize(prob: _cabi.Problem, partials_global: torch.Tensor) -> torch.Tensor:
     lib = _cabi.load()
     dev = partials_global.device
