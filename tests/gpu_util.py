@@ -43,5 +43,8 @@ def kernel_stats(z_cpu, y_cpu, *, tau, similarity, lam=0.0, t=2.0, topk=32, alph
                            row_offset=row_offset, n_rows=n_rows)
     whole = row_offset == 0 and (n_rows is None or n_rows == z.size(0))
     stats, partials, loss = Fn.forward_rows(z, y, prob, want_loss=whole)
-    idx = Fn.topk_indices(z, y, stats, prob) if topk >= 1 else None
+    # index sets are re-derived with the exact fp32 Gram: only meaningful for statistics of the exact paths
+    uses_tc = (dtype == torch.bfloat16 and z.size(1) == 256 and z.size(0) >= 256 and tau >= 0.025
+               and not (flags & 1) and (alpha == 0 or topk <= 32))
+    idx = Fn.topk_indices(z, y, stats, prob) if (topk >= 1 and not uses_tc) else None
     return dict(z=z, y=y, prob=prob, stats=stats, partials=partials, loss=loss, idx=idx)

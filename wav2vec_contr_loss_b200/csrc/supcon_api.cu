@@ -335,6 +335,10 @@ int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int3
   if (int rc = validate(p)) return rc;
   if (!z_all || !labels_all || !row_stats || !idx_out || p->topk < 1)
     return fail(SUPCON_E_INVALID, "bad arguments to supcon_topk_indices");
+  if (use_tc(p, false))
+    return fail(SUPCON_E_UNSUPPORTED,
+                "supcon_topk_indices re-derives the sets with the exact fp32 Gram; statistics of the bf16 tensor path "
+                "rank by the tcgen05 Gram -- pass SUPCON_FLAG_FORCE_EXACT to the forward and to this call");
   FfmaArgs a = make_ffma(p, z_all, labels_all, (void*)idx_out);
   a.row_stats = const_cast<float*>(row_stats);
   cudaError_t e = ffma_topk_indices(a, idx_out, reinterpret_cast<cudaStream_t>(stream));

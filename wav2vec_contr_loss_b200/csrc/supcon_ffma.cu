@@ -305,11 +305,6 @@ __global__ void __launch_bounds__(NT) ffma_fwd_kernel(FfmaArgs a) {
 // ---------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------
-struct ColCoef {  // per column (or row) quantities the H tile needs
-  float lse, rm, af, am, bp, thr;
-  int thr_idx, lab;
-};
-
 __device__ __forceinline__ void load_coef(const FfmaArgs& a, const GlobalCoef& g, int gidx, bool ok, float* f,
                                           int* n, int slot, int stride) {
   // layout: f[0]=lse f[1]=rm f[2]=af f[3]=am f[4]=bp f[5]=thr ; n[0]=thr_idx n[1]=lab

@@ -41,7 +41,7 @@ struct TcPlan {
   TcSched fwd_sched_local, fwd_sched_remote;   // two-phase forward (own columns first, then the others)
   bool two_phase;
   int local_ct0, local_cts, slots_local;
-  int n_pad, rows_pad, row_blocks, fwd_row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_splits, bwd_splits, merge_blocks;
+  int n_pad, rows_pad, row_blocks, fwd_row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_slots, bwd_slots, merge_blocks;
   size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
       off_scalars, off_topk_v, off_topk_i, off_part, total_bytes;
 };

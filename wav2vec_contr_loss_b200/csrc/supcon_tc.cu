@@ -3,17 +3,18 @@
 // exp / log-sum-exp and (backward) the formation of H = G + G^T, so the N x N
 // matrix never reaches HBM.
 //
-//   forward  : per CTA a 128-row block I and a range of 128-column tiles J.
-//              S_IJ = Z_I Z_J^T (16 x tcgen05.mma 128x128x16) into one of two
-//              TMEM buffers; two softmax warpgroups drain alternate buffers.
-//              Every similarity is <= 1, so exp uses the fixed maximum 1/tau
-//              (no online rescale).  Output: per-row partial sums
-//              per column split; a merge kernel turns them into row statistics.
-//   backward : per CTA a 128-row block I and a range of 64-column tiles J.
-//              S_IJ recomputed (tcgen05 128x64x16), H_IJ formed in registers
-//              from row/column coefficient vectors, written as bf16 into
-//              128B-swizzled smem, then dZ_I += H_IJ Z_J (tcgen05 128x256x16,
-//              Z_J tile reused MN-major) accumulating in TMEM.
+//   forward  : persistent CTAs walk (256-row block, 128-column tile) segments.  The two
+//              128-row blocks sit in tensor memory as MMA A operands; S_g = A_g Z_J^T
+//              (16 x tcgen05.mma 128x128x16, B = TMA-staged Z_J tile) lands in TMEM and
+//              warpgroup g reduces it from registers.  Every similarity is <= 1, so exp
+//              uses the fixed maximum 1/tau (no online rescale).  Output:
+//              per-row partial sums (+ top-K candidate lists) per segment; a merge
+//              kernel turns them into row statistics and the loss.
+//   backward : persistent CTAs walk (128-row block, 64-column tile) segments.  S_IJ is
+//              recomputed (A = Z_I in TMEM), H_IJ formed in registers from row/column
+//              coefficient vectors and written as packed bf16 over the S buffer in
+//              TMEM, then dZ_I += H_IJ Z_J (tcgen05 128x256x16, the same smem Z_J tile
+//              consumed MN-major) accumulates in TMEM.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM
 // alloc), warps 2..9 = eight softmax/epilogue warps (two warpgroups).
@@ -885,8 +886,8 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.bwd_col_tiles = (p->n_total + 63) / 64;
   pl.fwd_sched = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles, num_sms(), "SUPCON_TC_FWD_CTAS");
   pl.bwd_sched = make_sched(pl.row_blocks, pl.bwd_col_tiles, num_sms(), "SUPCON_TC_BWD_CTAS");
-  pl.fwd_splits = sched_max_slots(pl.fwd_sched, pl.fwd_row_blocks);
-  pl.bwd_splits = sched_max_slots(pl.bwd_sched, pl.row_blocks);
+  pl.fwd_slots = sched_max_slots(pl.fwd_sched, pl.fwd_row_blocks);
+  pl.bwd_slots = sched_max_slots(pl.bwd_sched, pl.row_blocks);
   // two-phase forward (multi-GPU overlap): phase 1 sweeps the rank's own columns, phase 2 the others
   pl.two_phase = (p->n_rows < p->n_total) && (p->row_offset % 128 == 0) && (p->n_rows % 128 == 0);
   pl.local_ct0 = p->row_offset / 128;
@@ -896,7 +897,7 @@ TcPlan tc_plan(const supcon_problem_t* p) {
     pl.fwd_sched_remote = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles - pl.local_cts, num_sms(), "SUPCON_TC_FWD_CTAS");
     pl.slots_local = sched_max_slots(pl.fwd_sched_local, pl.fwd_row_blocks);
     int both = pl.slots_local + sched_max_slots(pl.fwd_sched_remote, pl.fwd_row_blocks);
-    if (both > pl.fwd_splits) pl.fwd_splits = both;
+    if (both > pl.fwd_slots) pl.fwd_slots = both;
   }
   pl.merge_blocks = pl.rows_pad / 128;
   size_t off = 256;
@@ -911,11 +912,11 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.off_scalars = off; off += 256;
   const bool mine = p->alpha != 0.f && p->topk >= 1;
   const size_t kcap = mine ? (size_t)(p->topk < TC_KCAP ? p->topk : TC_KCAP) : 0;
-  pl.off_topk_v = off; off += align_up((size_t)pl.fwd_splits * pl.rows_pad * kcap * 4, 256);
-  pl.off_topk_i = off; off += align_up((size_t)pl.fwd_splits * pl.rows_pad * kcap * 4, 256);
+  pl.off_topk_v = off; off += align_up((size_t)pl.fwd_slots * pl.rows_pad * kcap * 4, 256);
+  pl.off_topk_i = off; off += align_up((size_t)pl.fwd_slots * pl.rows_pad * kcap * 4, 256);
   pl.off_part = off;
-  size_t fwd_part = (size_t)pl.fwd_splits * pl.rows_pad * 8 * sizeof(float);
-  size_t bwd_part = (size_t)pl.bwd_splits * pl.rows_pad * TD * sizeof(float);
+  size_t fwd_part = (size_t)pl.fwd_slots * pl.rows_pad * 8 * sizeof(float);
+  size_t bwd_part = (size_t)pl.bwd_slots * pl.rows_pad * TD * sizeof(float);
   off += align_up(fwd_part > bwd_part ? fwd_part : bwd_part, 256);
   pl.total_bytes = off;
   return pl;
