@@ -838,13 +838,14 @@ int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-TcSched make_sched(int row_blocks, int col_tiles, int num_sms, const char* env_ctas) {
+TcSched make_sched(int row_blocks, int col_tiles, int num_sms, const char* env_ctas, int leave_free = 0) {
   TcSched sc;
   sc.T = col_tiles;
   sc.U = (long long)row_blocks * col_tiles;
   // two CTAs' worth of work per SM: the hardware scheduler evens out SM-to-SM speed differences
   // (measured: rank share of N/8 rows 0.714 -> 0.694 ms), as long as a CTA still gets >= 32 tiles
   long long p = env_int(env_ctas, 0);
+  if (p <= 0 && leave_free > 0) p = num_sms > leave_free ? num_sms - leave_free : 1;   // one CTA per used SM
   if (p <= 0) p = (sc.U / (2LL * num_sms) >= 32) ? 2LL * num_sms : num_sms;
   if (p > sc.U) p = sc.U;
   if (p < 1) p = 1;
@@ -893,7 +894,10 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.local_ct0 = p->row_offset / 128;
   pl.local_cts = p->n_rows / 128;
   if (pl.two_phase) {
-    pl.fwd_sched_local = make_sched(pl.fwd_row_blocks, pl.local_cts, num_sms(), "SUPCON_TC_FWD_CTAS");
+    // the own-column phase runs beside the NCCL all-gather kernel: leave SMs free for its channels (a CTA of
+    // this kernel fills an SM, so the collective could not co-reside and the two would serialise)
+    pl.fwd_sched_local = make_sched(pl.fwd_row_blocks, pl.local_cts, num_sms(), "SUPCON_TC_LOCAL_CTAS",
+                                    env_int("SUPCON_TC_LOCAL_FREE_SMS", 32));
     pl.fwd_sched_remote = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles - pl.local_cts, num_sms(), "SUPCON_TC_FWD_CTAS");
     pl.slots_local = sched_max_slots(pl.fwd_sched_local, pl.fwd_row_blocks);
     int both = pl.slots_local + sched_max_slots(pl.fwd_sched_remote, pl.fwd_row_blocks);
