@@ -397,3 +397,42 @@ def test_two_phase_forward_equals_single_phase(cuda_device, sim, lam, alpha, k):
         assert torch.equal(s1.view(torch.int32)[:, [2, 3, 5]], s2.view(torch.int32)[:, [2, 3, 5]])   # counts, threshold idx
         assert torch.allclose(s1[:, [0, 1, 6, 7]], s2[:, [0, 1, 6, 7]], rtol=1e-5, atol=1e-6)       # sums: order differs
         assert torch.allclose(p1, p2, rtol=1e-6)
+
+
+@pytest.mark.parametrize("n", [100, 200])
+def test_bf16_small_and_mid_batches_take_exact_kernels(cuda_device, n):
+    """bf16 z below the tensor-path threshold: N=100 -> single-launch cluster kernel, N=200 -> tiled FFMA kernels."""
+    x, y = O.make_inputs(n, 256, "iso", classes=3)
+    zb = F.normalize(x, dim=1).to(torch.bfloat16)
+    kw = dict(tau=0.07, similarity="geodesic", lam=0.05, topk=7, alpha=0.5)
+    loss, dz = G.kernel_loss_and_grad(zb, y, dtype=torch.bfloat16, **kw)
+    ref = G.oracle_for(zb.float(), y, **kw)
+    assert loss == pytest.approx(ref["loss"], rel=1e-5)          # fp32 math on the bf16-rounded inputs
+    assert G.rel_err(dz, ref["dz"]) < 2 * TOL_BF16               # dz rounded to bf16 by autograd
+
+
+def test_sharded_loss_single_rank_nccl(cuda_device):
+    """ShardedSupConLoss on a world_size-1 NCCL group: the GPU code path of the distributed module
+    (in-place all-gather on the side stream, two-phase entry points, stats exchange) == SupConBinaryLoss."""
+    import socket
+    import torch.distributed as dist
+    from wav2vec_contr_loss_b200 import SupConBinaryLoss
+    from wav2vec_contr_loss_b200.distributed import ShardedSupConLoss
+    if dist.is_initialized():
+        pytest.skip("a process group already exists")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                            device_id=cuda_device)
+    try:
+        x, y = O.make_inputs(512, 256, "iso")
+        for dtype in (torch.float32, torch.bfloat16):
+            z1 = F.normalize(x, dim=1).to(cuda_device).to(dtype).requires_grad_(True)
+            z2 = z1.detach().clone().requires_grad_(True)
+            yy = y.to(cuda_device)
+            a = ShardedSupConLoss(0.07, "cosine", 0.05)(z1, yy, topk_neg=15, alpha=0.0)
+            b = SupConBinaryLoss(0.07, "cosine", 0.05)(z2, yy, topk_neg=15, alpha=0.0)
+            (2.0 * a).backward(); (2.0 * b).backward()
+            assert float(a) == pytest.approx(float(b), rel=1e-6)
+            assert G.rel_err(z1.grad.float().cpu(), z2.grad.float().cpu()) < 1e-5
+    finally:
+        dist.destroy_process_group()
