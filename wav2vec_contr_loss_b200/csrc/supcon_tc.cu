@@ -896,8 +896,9 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   if (pl.two_phase) {
     // the own-column phase runs beside the NCCL all-gather kernel: leave SMs free for its channels (a CTA of
     // this kernel fills an SM, so the collective could not co-reside and the two would serialise)
-    pl.fwd_sched_local = make_sched(pl.fwd_row_blocks, pl.local_cts, num_sms(), "SUPCON_TC_LOCAL_CTAS",
-                                    env_int("SUPCON_TC_LOCAL_FREE_SMS", 32));
+    // (only when that phase is short, i.e. the rank owns at most a quarter of the columns)
+    const int free_sms = (4 * pl.local_cts <= pl.fwd_col_tiles) ? env_int("SUPCON_TC_LOCAL_FREE_SMS", 32) : 0;
+    pl.fwd_sched_local = make_sched(pl.fwd_row_blocks, pl.local_cts, num_sms(), "SUPCON_TC_LOCAL_CTAS", free_sms);
     pl.fwd_sched_remote = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles - pl.local_cts, num_sms(), "SUPCON_TC_FWD_CTAS");
     pl.slots_local = sched_max_slots(pl.fwd_sched_local, pl.fwd_row_blocks);
     int both = pl.slots_local + sched_max_slots(pl.fwd_sched_remote, pl.fwd_row_blocks);
