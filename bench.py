@@ -360,10 +360,10 @@ def main():
         else:
             stats_all = stats
         dz = Fn.backward_rows(z_all, y_all, stats_all, partials, None, prob, out_dtype=tdtype)
-        # kernels of libsupcon_b200.so per step on the tensor path: prep_fwd, tc_fwd, merge, prep_bwd, tc_bwd,
-        # reduce; with several ranks the forward runs in two phases (prep + tc_fwd twice) and a finalize kernel
-        # turns the exchanged partial sums into the loss
-        launches["count"] += 6 + (3 if world > 1 else 0)
+        # kernels of libsupcon_b200.so per step on the tensor path: prep_fwd, label_table, tc_fwd, merge, prep_bwd,
+        # tc_bwd, reduce; with several ranks the forward runs in two phases (prep + label_table + tc_fwd twice) and a
+        # finalize kernel turns the exchanged partial sums into the loss
+        launches["count"] += 7 + (4 if world > 1 else 0)
         return loss, dz
 
     class Stepper:

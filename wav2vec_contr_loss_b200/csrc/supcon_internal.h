@@ -43,12 +43,16 @@ struct TcPlan {
   int local_ct0, local_cts, slots_local;
   int n_pad, rows_pad, row_blocks, fwd_row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_slots, bwd_slots, merge_blocks;
   size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
-      off_scalars, off_topk_v, off_topk_i, off_part, total_bytes;
+      off_scalars, off_hkeys, off_hcounts, off_topk_v, off_topk_i, off_part, total_bytes;
+  uint32_t hash_size;
 };
 struct TcFwdArgs {
   const int32_t* lab_pad;
   const float* nrm_pad;
-  float* part;       // [splits][rows_pad][8]
+  const unsigned long long* hkeys;   // label -> class size table (tc_prep_fwd_kernel)
+  const int* hcounts;
+  uint32_t hmask;
+  float* part;       // [slots][rows_pad][8]
   float* topk_v;     // [splits][rows_pad][kcap]  per-split hard-negative candidates (mining)
   int32_t* topk_i;
   TcSched sched;

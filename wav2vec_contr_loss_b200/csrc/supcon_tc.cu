@@ -78,6 +78,24 @@ __device__ __forceinline__ float geodesic_slope_fast(float c) {
 // ---------------------------------------------------------------------------
 // prep: padded labels / squared norms (forward) and column coefficients (backward)
 // ---------------------------------------------------------------------------
+// Class sizes without a per-pair counter in the hot loop: every label is inserted into an open-addressing
+// table (key slot = 1<<32 | label, linear probing) with a count; a row's |pos_i| is its label's count - 1.
+__device__ __forceinline__ uint32_t label_hash(int32_t lab, uint32_t mask) {
+  uint32_t h = (uint32_t)lab * 2654435761u;
+  return (h ^ (h >> 15)) & mask;
+}
+__device__ __forceinline__ int label_table_count(const unsigned long long* keys, const int* counts, uint32_t mask,
+                                                 int32_t lab) {
+  const unsigned long long want = (1ull << 32) | (unsigned long long)(uint32_t)lab;
+  uint32_t h = label_hash(lab, mask);
+  for (;;) {
+    const unsigned long long k = keys[h];
+    if (k == want) return counts[h];
+    if (k == 0ull) return 0;
+    h = (h + 1) & mask;
+  }
+}
+
 __global__ void tc_prep_fwd_kernel(const __nv_bfloat16* __restrict__ z, const int32_t* __restrict__ labels, int n,
                                    int n_pad, int d, int32_t* __restrict__ lab_pad, float* __restrict__ nrm_pad,
                                    int want_norms, int j_lo = 0, int ex_lo = 0x7fffffff, int ex_len = 0) {
@@ -94,6 +112,28 @@ __global__ void tc_prep_fwd_kernel(const __nv_bfloat16* __restrict__ z, const in
   if (lane == 0) {
     lab_pad[warp] = warp < n ? labels[warp] : 0;
     if (want_norms) nrm_pad[warp] = warp < n ? s : 0.f;
+  }
+}
+
+// class sizes: one thread per column of [j_lo, n) minus the excluded window; lanes holding the same label are
+// aggregated (__match_any_sync) so a binary batch costs two atomics per warp instead of 32 on two addresses
+__global__ void tc_label_table_kernel(const int32_t* __restrict__ labels, int n, unsigned long long* hkeys,
+                                      int* hcounts, uint32_t hmask, int j_lo, int ex_lo, int ex_len) {
+  int j = j_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ex_lo) j += ex_len;
+  const bool ok = j < n;
+  const unsigned active = __ballot_sync(0xffffffffu, ok);
+  if (!ok) return;
+  const int32_t lab = labels[j];
+  const unsigned peers = __match_any_sync(active, lab);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+    const unsigned long long want = (1ull << 32) | (unsigned long long)(uint32_t)lab;
+    uint32_t h = label_hash(lab, hmask);
+    for (;;) {
+      const unsigned long long prev = atomicCAS(&hkeys[h], 0ull, want);
+      if (prev == 0ull || prev == want) { atomicAdd(&hcounts[h], __popc(peers)); break; }
+      h = (h + 1) & hmask;
+    }
   }
 }
 
@@ -144,7 +184,6 @@ __host__ __device__ inline int sched_cta_of(const TcSched& s, long long u) {
 // ---------------------------------------------------------------------------
 struct RowSums {
   float sum_all, sum_pos_s, wsum;
-  int npos;
   float sum_pos_e;   // mining: sum of e over positives
 };
 
@@ -200,7 +239,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
       }
       st.sum_all += ex;
       if (pos) {
-        st.sum_pos_s += s; st.npos++;
+        st.sum_pos_s += s;
         if (MINE) st.sum_pos_e += ex;
       }
       if (MINE) {
@@ -367,7 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
       const int lab_r = a.lab_pad[min(gi, a.n_pad - 1)];
       const float nrm_r = UNI ? a.nrm_pad[min(gi, a.n_pad - 1)] : 0.f;
       RowSums st;
-      st.sum_all = 0.f; st.sum_pos_s = 0.f; st.wsum = 0.f; st.npos = 0; st.sum_pos_e = 0.f;
+      st.sum_all = 0.f; st.sum_pos_s = 0.f; st.wsum = 0.f; st.sum_pos_e = 0.f;
       MineState ms;
       ms.thr = -INFINITY; ms.cnt = 0;
       for (int t = 0; t < nt; ++t, ++g) {
@@ -403,7 +442,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
         const int slot_out = a.slot_base + (int)blockIdx.x - sched_cta_of(sc, (long long)rb * sc.T);
         const int64_t rec = (int64_t)slot_out * a.rows_pad + (gi - a.row_offset);
         float* out = a.part + rec * 8;
-        *reinterpret_cast<float4*>(out) = make_float4(st.sum_all, st.sum_pos_s, st.wsum, __int_as_float(st.npos));
+        *reinterpret_cast<float4*>(out) = make_float4(st.sum_all, st.sum_pos_s, st.wsum, 0.f);
         *reinterpret_cast<float4*>(out + 4) = make_float4(st.sum_pos_e, __int_as_float(ms.cnt), 0.f, 0.f);
         if (MINE) {
           for (int e = 0; e < ms.cnt; ++e) {
@@ -427,7 +466,7 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
   double l_full = 0.0, c_full = 0.0, l_mined = 0.0, c_mined = 0.0, w = 0.0;
   if (lr < a.n_rows) {
     float sum_all = 0.f, sum_pos_s = 0.f, wsum = 0.f, sum_pos_e = 0.f;
-    int npos = 0;
+    const int npos = label_table_count(a.hkeys, a.hcounts, a.hmask, a.lab_pad[a.row_offset + lr]) - 1;
     // partial records of this row: one per CTA whose unit range touches the row's 256-row block,
     // in CTA order = ascending column order
     const int rb = lr / (2 * TBM);
@@ -444,7 +483,7 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
       for (int s = slot_lo[ps]; s < slot_lo[ps] + slot_n[ps]; ++s) {
         const float* rec = a.part + ((int64_t)s * a.rows_pad + lr) * 8;
         const float4 v = *reinterpret_cast<const float4*>(rec);
-        sum_all += v.x; sum_pos_s += v.y; wsum += v.z; npos += __float_as_int(v.w);
+        sum_all += v.x; sum_pos_s += v.y; wsum += v.z;
         sum_pos_e += rec[4];
       }
     const int nneg = a.n_total - 1 - npos;
@@ -915,6 +954,11 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.off_colThr = off; off += align_up((size_t)pl.n_pad * 4, 256);
   pl.off_colThrIdx = off; off += align_up((size_t)pl.n_pad * 4, 256);
   pl.off_scalars = off; off += 256;
+  uint32_t hsize = 1024;
+  while (hsize < 2u * (uint32_t)p->n_total) hsize <<= 1;
+  pl.hash_size = hsize;
+  pl.off_hkeys = off; off += (size_t)hsize * 8;      // keys then counts: one memset clears both
+  pl.off_hcounts = off; off += (size_t)hsize * 4;
   const bool mine = p->alpha != 0.f && p->topk >= 1;
   const size_t kcap = mine ? (size_t)(p->topk < TC_KCAP ? p->topk : TC_KCAP) : 0;
   pl.off_topk_v = off; off += align_up((size_t)pl.fwd_slots * pl.rows_pad * kcap * 4, 256);
@@ -966,6 +1010,7 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
   cudaError_t e = cudaSuccess;
   if (phase != 2) {
     e = cudaMemsetAsync(workspace, 0, 256, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws + pl.off_hkeys, 0, (size_t)pl.hash_size * 12, stream);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
   }
   const bool uni = p->lambda_uni > 0.f;
@@ -982,8 +1027,19 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
                                                          reinterpret_cast<int32_t*>(ws + pl.off_lab),
                                                          reinterpret_cast<float*>(ws + pl.off_nrm), uni ? 1 : 0, j_lo,
                                                          ex_lo, ex_len);
+    // class-size table over the (real) columns of this phase
+    int jn_lo = j_lo, jn_ex_lo = ex_lo, jn_ex_len = ex_len, jn_count = p->n_total;
+    if (phase == 1) { jn_count = p->n_rows; jn_ex_lo = jn_lo + jn_count; jn_ex_len = p->n_total; }
+    if (phase == 2) { jn_count = p->n_total - p->n_rows; jn_ex_len = p->n_rows; }
+    if (jn_count > 0)
+      tc_label_table_kernel<<<(jn_count + 255) / 256, 256, 0, stream>>>(
+          labels_all, p->n_total, reinterpret_cast<unsigned long long*>(ws + pl.off_hkeys),
+          reinterpret_cast<int*>(ws + pl.off_hcounts), pl.hash_size - 1, jn_lo, jn_ex_lo, jn_ex_len);
   }
   TcFwdArgs a;
+  a.hkeys = reinterpret_cast<const unsigned long long*>(ws + pl.off_hkeys);
+  a.hcounts = reinterpret_cast<const int*>(ws + pl.off_hcounts);
+  a.hmask = pl.hash_size - 1;
   a.ct_base = 0; a.ex_lo = 0x7fffffff; a.ex_len = 0; a.slot_base = 0;
   a.sched_b.P = 0; a.sched_b.T = 1; a.sched_b.U = 1; a.slot_base_b = 0;
   a.lab_pad = reinterpret_cast<const int32_t*>(ws + pl.off_lab);
