@@ -60,7 +60,7 @@ bool use_tc(const supcon_problem_t* p, bool backward) {
 }
 
 size_t workspace_need(const supcon_problem_t* p) {
-  size_t need = ffma_workspace_bytes(p->n_rows);
+  size_t need = ffma_workspace_bytes(p);
   if (!(p->flags & SUPCON_FLAG_FORCE_EXACT) && tc_supported(p)) {
     size_t t = tc_plan(p).total_bytes;
     if (t > need) need = t;
@@ -90,12 +90,13 @@ SmallArgs make_small(const supcon_problem_t* p, const void* z, const int32_t* la
   return s;
 }
 
-FfmaArgs make_ffma(const supcon_problem_t* p, const void* z, const int32_t* labels, void* ws) {
+FfmaArgs make_ffma(const supcon_problem_t* p, const void* z, const int32_t* labels, void* ws, bool backward = false,
+                   bool use_plan = true) {
   FfmaArgs a;
   memset(&a, 0, sizeof(a));
   a.z = z; a.labels = labels;
-  a.ticket = reinterpret_cast<unsigned*>(ws);
-  a.block_partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
+  a.splits = 1; a.col_tiles = (p->n_total + 63) / 64; a.rows_pad = (p->n_rows + 63) / 64 * 64;
+  if (use_plan && ws) ffma_bind_plan(a, ffma_plan(p), ws, backward);
   a.n_total = p->n_total; a.row_offset = p->row_offset; a.n_rows = p->n_rows; a.d = p->d;
   a.z_dtype = p->z_dtype; a.similarity = p->similarity; a.topk = p->topk < 0 ? 0 : p->topk;
   a.mine = needs_mining(p) ? 1 : 0;
@@ -260,7 +261,9 @@ int supcon_backward_rows(const supcon_problem_t* p, const void* z_all, const int
     if (rc) return fail(rc, "tc_backward: %s", err);
     return 0;
   }
-  FfmaArgs a = make_ffma(p, z_all, labels_all, workspace ? workspace : (void*)dz_out);
+  if (!workspace || workspace_bytes < workspace_need(p))
+    return fail(SUPCON_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, workspace_need(p));
+  FfmaArgs a = make_ffma(p, z_all, labels_all, workspace, /*backward=*/true);
   a.stats_all = stats_all;
   a.partials = const_cast<double*>(partials_global);
   a.grad_out = grad_out; a.dz_out = dz_out;
@@ -339,7 +342,7 @@ int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int3
     return fail(SUPCON_E_UNSUPPORTED,
                 "supcon_topk_indices re-derives the sets with the exact fp32 Gram; statistics of the bf16 tensor path "
                 "rank by the tcgen05 Gram -- pass SUPCON_FLAG_FORCE_EXACT to the forward and to this call");
-  FfmaArgs a = make_ffma(p, z_all, labels_all, (void*)idx_out);
+  FfmaArgs a = make_ffma(p, z_all, labels_all, nullptr, false, /*use_plan=*/false);
   a.row_stats = const_cast<float*>(row_stats);
   cudaError_t e = ffma_topk_indices(a, idx_out, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "ffma_topk_indices");

@@ -138,6 +138,11 @@ __global__ void __launch_bounds__(NT) ffma_fwd_kernel(FfmaArgs a) {
   int bound_i = -1;
   int rounds_total = 1;
 
+  // column range of this CTA (blockIdx.y = column split; one split = the whole sweep)
+  const int split = blockIdx.y;
+  const int c_lo = (int)(((int64_t)a.col_tiles * split) / a.splits) * BN;
+  const int c_hi = min(a.n_total, (int)(((int64_t)a.col_tiles * (split + 1)) / a.splits) * BN);
+
   float acc[4][4];
   for (int round = 0; round < rounds_total; ++round) {
     const bool first = round == 0;
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(NT) ffma_fwd_kernel(FfmaArgs a) {
     const bool row_mines = mine && row_ok && (first || nneg > a.topk);
     if (tid < BM) cnt[tid] = 0;
     __syncthreads();
-    for (int col0 = 0; col0 < a.n_total; col0 += BN) {
+    for (int col0 = c_lo; col0 < c_hi; col0 += BN) {
       gram_tile<T>(z, a.d, a.vec_ok, row0, row_end, col0, a.n_total, As, Bs, acc, nrm_r, nrm_c, uni && first);
       if (tid < BN) lab_c[tid] = (col0 + tid < a.n_total) ? a.labels[col0 + tid] : 0;
       __syncthreads();  // norms + labels visible
@@ -250,6 +255,23 @@ __global__ void __launch_bounds__(NT) ffma_fwd_kernel(FfmaArgs a) {
       }
       int more = (mine && row_ok && nneg > a.topk && a.topk > a.kcap) ? 1 : 0;
       if (__syncthreads_or(more)) rounds_total = (a.topk + a.kcap - 1) / a.kcap;
+      if (a.splits > 1) {
+        // column-split launch: leave this range's partial record (+ its candidate list); the merge kernel
+        // combines the ranges (online-max merge) and finishes the loss
+        if (pq == 0 && row_ok) {
+          const int64_t rec = (int64_t)split * a.rows_pad + (gi - a.row_offset);
+          float* out = a.part + rec * 8;
+          out[0] = M; out[1] = sum_all; out[2] = sum_pos_e; out[3] = sum_pos_s; out[4] = wsum;
+          reinterpret_cast<int*>(out)[5] = npos; reinterpret_cast<int*>(out)[6] = nneg;
+          const int c = mine ? cnt[pr] : 0;
+          reinterpret_cast<int*>(out)[7] = c;
+          for (int t = 0; t < c; ++t) {
+            a.lv_part[rec * a.kcap + t] = lv[pr * a.kcap + t];
+            a.li_part[rec * a.kcap + t] = li[pr * a.kcap + t];
+          }
+        }
+        return;
+      }
     }
     if (mine) {
       // close this round: fold its list into sum_top, publish the new bound to the row's threads
@@ -300,6 +322,91 @@ __global__ void __launch_bounds__(NT) ffma_fwd_kernel(FfmaArgs a) {
   __syncthreads();
   FinishArgs fa{a.block_partials, a.ticket, a.partials, a.loss_out, a.n_total, a.tau, a.alpha, a.lambda_uni, a.uni_t};
   block_partials_and_finish(fa, red, BM);
+}
+
+// combine the column splits of ffma_fwd_kernel: online-max merge of the sums, (value desc, index asc) merge of
+// the candidate lists, then the same row statistics / loss partials as the single-sweep kernel
+__global__ void __launch_bounds__(128) ffma_fwd_merge_kernel(FfmaArgs a) {
+  __shared__ double red[5 * 128];
+  const int lr = blockIdx.x * 128 + threadIdx.x;
+  double l_full = 0.0, c_full = 0.0, l_mined = 0.0, c_mined = 0.0, w = 0.0;
+  if (lr < a.n_rows) {
+    float M = -INFINITY;
+    for (int s = 0; s < a.splits; ++s) M = fmaxf(M, a.part[((int64_t)s * a.rows_pad + lr) * 8]);
+    float sum_all = 0.f, sum_pos_e = 0.f, sum_pos_s = 0.f, wsum = 0.f;
+    int npos = 0, nneg = 0;
+    for (int s = 0; s < a.splits; ++s) {
+      const float* rec = a.part + ((int64_t)s * a.rows_pad + lr) * 8;
+      const float f = (rec[0] == -INFINITY) ? 0.f : expf(rec[0] - M);
+      sum_all += rec[1] * f; sum_pos_e += rec[2] * f; sum_pos_s += rec[3]; wsum += rec[4];
+      npos += reinterpret_cast<const int*>(rec)[5]; nneg += reinterpret_cast<const int*>(rec)[6];
+    }
+    const float lse = M + logf(sum_all);
+    float lse_m = lse, thr_val = -INFINITY;
+    int thr_idx = SUPCON_INT_MAX;
+    if (a.mine && nneg > a.topk) {
+      const int K = a.topk;   // <= kcap <= 128 when the sweep is split
+      float mv[128];
+      int mi[128];
+      int cnt = 0;
+      for (int s = 0; s < a.splits; ++s) {
+        const int64_t rec = (int64_t)s * a.rows_pad + lr;
+        const int c = reinterpret_cast<const int*>(a.part + rec * 8)[7];
+        for (int e = 0; e < c; ++e) {
+          const float v = a.lv_part[rec * a.kcap + e];
+          const int ix = a.li_part[rec * a.kcap + e];
+          int p;
+          if (cnt < K) p = cnt++;
+          else if (v > mv[K - 1] || (v == mv[K - 1] && ix < mi[K - 1])) p = K - 1;
+          else break;
+          while (p > 0 && (mv[p - 1] < v || (mv[p - 1] == v && mi[p - 1] > ix))) { mv[p] = mv[p - 1]; mi[p] = mi[p - 1]; --p; }
+          mv[p] = v; mi[p] = ix;
+        }
+      }
+      float sum_top = 0.f;
+      for (int e = 0; e < K; ++e) sum_top += expf(__fdiv_rn(mv[e], a.tau) - M);
+      lse_m = M + logf(sum_pos_e + sum_top);
+      thr_val = mv[K - 1];
+      thr_idx = mi[K - 1];
+    } else if (a.topk < 1) {
+      thr_val = INFINITY; thr_idx = -1;
+    }
+    const float pos_mean = (npos > 0) ? __fdiv_rn(__fdiv_rn(sum_pos_s, a.tau), (float)npos) : 0.f;
+    float* so = a.row_stats + (int64_t)lr * SUPCON_STATS_STRIDE;
+    so[SUPCON_ST_LSE] = lse; so[SUPCON_ST_LSE_M] = lse_m;
+    reinterpret_cast<int*>(so)[SUPCON_ST_NPOS] = npos; reinterpret_cast<int*>(so)[SUPCON_ST_NNEG] = nneg;
+    so[SUPCON_ST_THR_VAL] = thr_val; reinterpret_cast<int*>(so)[SUPCON_ST_THR_IDX] = thr_idx;
+    so[SUPCON_ST_WSUM] = wsum; so[SUPCON_ST_POS_MEAN] = pos_mean;
+    if (npos > 0) {
+      l_full = (double)(lse - pos_mean); c_full = 1.0;
+      if (nneg > 0 && a.topk >= 1) { l_mined = (double)(lse_m - pos_mean); c_mined = 1.0; }
+    }
+    w = (double)wsum;
+  }
+  red[0 * 128 + threadIdx.x] = l_full; red[1 * 128 + threadIdx.x] = c_full; red[2 * 128 + threadIdx.x] = l_mined;
+  red[3 * 128 + threadIdx.x] = c_mined; red[4 * 128 + threadIdx.x] = w;
+  __syncthreads();
+  FinishArgs fa{a.block_partials, a.ticket, a.partials, a.loss_out, a.n_total, a.tau, a.alpha, a.lambda_uni, a.uni_t};
+  block_partials_and_finish(fa, red, 128);
+}
+
+// sum the column splits of ffma_bwd_kernel, add the uniformity diagonal term, scale by grad_out, convert
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) ffma_bwd_reduce_kernel(FfmaArgs a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)a.n_rows * a.d) return;
+  const int lr = (int)(idx / a.d), dd = (int)(idx % a.d);
+  float v = 0.f;
+  for (int s = 0; s < a.splits; ++s) v += a.dz_part[((int64_t)s * a.rows_pad + lr) * a.d + dd];
+  const GlobalCoef g = global_coef(a.partials, a.n_total, a.tau, a.alpha, a.lambda_uni, a.uni_t);
+  const int gi = a.row_offset + lr;
+  if (g.cu != 0.f)
+    v = fmaf(g.cu * a.stats_all[(int64_t)gi * SUPCON_STATS_STRIDE + SUPCON_ST_WSUM],
+             ld_elem<T>(reinterpret_cast<const T*>(a.z) + (int64_t)gi * a.d + dd), v);
+  v *= a.grad_out ? *a.grad_out : 1.0f;
+  TO* out = reinterpret_cast<TO*>(a.dz_out);
+  if constexpr (sizeof(TO) == 4) out[idx] = v;
+  else out[idx] = __float2bfloat16(v);
 }
 
 // ---------------------------------------------------------------------------
@@ -363,8 +470,11 @@ __global__ void __launch_bounds__(NT) ffma_bwd_kernel(FfmaArgs a) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) dz[i][e] = 0.f;
 
+  const int split = blockIdx.z;
+  const int c_lo = (int)(((int64_t)a.col_tiles * split) / a.splits) * BN;
+  const int c_hi = min(a.n_total, (int)(((int64_t)a.col_tiles * (split + 1)) / a.splits) * BN);
   float acc[4][4];
-  for (int col0 = 0; col0 < a.n_total; col0 += BN) {
+  for (int col0 = c_lo; col0 < c_hi; col0 += BN) {
     gram_tile<T>(z, a.d, a.vec_ok, row0, row_end, col0, a.n_total, As, Bs, acc, nrm_r, nrm_c, uni);
     if (tid < BN) load_coef(a, g, col0 + tid, col0 + tid < a.n_total, cf, cn, tid, BN);
     // stage Z_J[:, dc0:dc0+DC] (fp32) for the H.Z product
@@ -433,6 +543,22 @@ __global__ void __launch_bounds__(NT) ffma_bwd_kernel(FfmaArgs a) {
     __syncthreads();
   }
 
+  if (a.splits > 1) {   // raw partial sums of this column range; ffma_bwd_reduce_kernel finishes them
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gi = row0 + ty + 16 * i;
+      if (gi >= row_end) continue;
+      float* prow = a.dz_part + ((int64_t)split * a.rows_pad + (gi - a.row_offset)) * a.d;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int dd = dc0 + 4 * tx + 64 * q + e;
+          if (dd < a.d) prow[dd] = dz[i][4 * q + e];
+        }
+    }
+    return;
+  }
   const float gscale = a.grad_out ? *a.grad_out : 1.0f;
   TO* out = reinterpret_cast<TO*>(a.dz_out);
 #pragma unroll
@@ -526,33 +652,95 @@ cudaError_t set_smem(K kernel, size_t bytes) {
 
 int ffma_kcap() { return 128; }
 
-size_t ffma_workspace_bytes(int n_rows) {
-  int blocks = (n_rows + BM - 1) / BM;
-  return 256 + (size_t)blocks * SUPCON_N_PARTIALS * sizeof(double);
+namespace {
+int ffma_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+}  // namespace
+
+// Column splits: with 64-row blocks a mid-size batch (N ~ 1k) gives only a handful of CTAs, so the column
+// sweep is cut into ranges (blockIdx.y / .z) until ~2 CTAs per SM exist; partial records / partial dz go
+// through the workspace and a merge / reduce kernel.
+FfmaPlan ffma_plan(const supcon_problem_t* p) {
+  FfmaPlan pl;
+  const int row_blocks = (p->n_rows + BM - 1) / BM;
+  pl.col_tiles = (p->n_total + BN - 1) / BN;
+  pl.rows_pad = row_blocks * BM;
+  const bool mine = p->alpha != 0.f && p->topk >= 1;
+  const int topk = p->topk < 0 ? 0 : p->topk;
+  pl.kcap = mine ? (topk < ffma_kcap() ? topk : ffma_kcap()) : 0;
+  const int dchunks = (p->d + DC - 1) / DC;
+  const int max_s = pl.col_tiles / 4 > 0 ? pl.col_tiles / 4 : 1;
+  int sf = (2 * ffma_num_sms()) / row_blocks;
+  int sb = (2 * ffma_num_sms()) / (row_blocks * dchunks);
+  if (mine && topk > ffma_kcap()) sf = 1;   // multi-round selection needs the whole sweep in one CTA
+  pl.fwd_splits = sf < 1 ? 1 : (sf > max_s ? max_s : sf);
+  pl.bwd_splits = sb < 1 ? 1 : (sb > max_s ? max_s : sb);
+  if (pl.fwd_splits > 64) pl.fwd_splits = 64;
+  if (pl.bwd_splits > 64) pl.bwd_splits = 64;
+  pl.merge_blocks = (p->n_rows + 127) / 128;
+  size_t off = 256;
+  const int finish_blocks = row_blocks > pl.merge_blocks ? row_blocks : pl.merge_blocks;
+  pl.off_block_partials = off; off += up256((size_t)finish_blocks * SUPCON_N_PARTIALS * sizeof(double));
+  pl.off_part = off; off += up256(pl.fwd_splits > 1 ? (size_t)pl.fwd_splits * pl.rows_pad * 8 * 4 : 0);
+  pl.off_lv = off; off += up256(pl.fwd_splits > 1 ? (size_t)pl.fwd_splits * pl.rows_pad * pl.kcap * 4 : 0);
+  pl.off_li = off; off += up256(pl.fwd_splits > 1 ? (size_t)pl.fwd_splits * pl.rows_pad * pl.kcap * 4 : 0);
+  pl.off_dz = off; off += up256(pl.bwd_splits > 1 ? (size_t)pl.bwd_splits * pl.rows_pad * p->d * 4 : 0);
+  pl.total_bytes = off;
+  return pl;
+}
+
+size_t ffma_workspace_bytes(const supcon_problem_t* p) { return ffma_plan(p).total_bytes; }
+
+void ffma_bind_plan(FfmaArgs& a, const FfmaPlan& pl, void* workspace, bool backward) {
+  char* ws = reinterpret_cast<char*>(workspace);
+  a.ticket = reinterpret_cast<unsigned*>(ws);
+  a.block_partials = reinterpret_cast<double*>(ws + pl.off_block_partials);
+  a.part = reinterpret_cast<float*>(ws + pl.off_part);
+  a.lv_part = reinterpret_cast<float*>(ws + pl.off_lv);
+  a.li_part = reinterpret_cast<int*>(ws + pl.off_li);
+  a.dz_part = reinterpret_cast<float*>(ws + pl.off_dz);
+  a.col_tiles = pl.col_tiles;
+  a.rows_pad = pl.rows_pad;
+  a.splits = backward ? pl.bwd_splits : pl.fwd_splits;
 }
 
 cudaError_t ffma_forward(const FfmaArgs& a, cudaStream_t stream) {
-  const int blocks = (a.n_rows + BM - 1) / BM;
+  dim3 grid((a.n_rows + BM - 1) / BM, a.splits);
   const size_t smem = fwd_smem_bytes(a.kcap);
   cudaError_t e;
   if (a.z_dtype == SUPCON_BF16) {
     if ((e = set_smem(ffma_fwd_kernel<__nv_bfloat16>, smem)) != cudaSuccess) return e;
-    ffma_fwd_kernel<__nv_bfloat16><<<blocks, NT, smem, stream>>>(a);
+    ffma_fwd_kernel<__nv_bfloat16><<<grid, NT, smem, stream>>>(a);
   } else {
     if ((e = set_smem(ffma_fwd_kernel<float>, smem)) != cudaSuccess) return e;
-    ffma_fwd_kernel<float><<<blocks, NT, smem, stream>>>(a);
+    ffma_fwd_kernel<float><<<grid, NT, smem, stream>>>(a);
   }
-  return cudaGetLastError();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (a.splits > 1) {
+    ffma_fwd_merge_kernel<<<(a.n_rows + 127) / 128, 128, 0, stream>>>(a);
+    e = cudaGetLastError();
+  }
+  return e;
 }
 
 cudaError_t ffma_backward(const FfmaArgs& a, int dz_dtype, cudaStream_t stream) {
-  dim3 grid((a.n_rows + BM - 1) / BM, (a.d + DC - 1) / DC);
+  dim3 grid((a.n_rows + BM - 1) / BM, (a.d + DC - 1) / DC, a.splits);
   const size_t smem = bwd_smem_bytes();
+  const int rblocks = (int)(((int64_t)a.n_rows * a.d + 255) / 256);
   cudaError_t e;
 #define SUPCON_LAUNCH_BWD(TI, TO)                                              \
   do {                                                                         \
     if ((e = set_smem(ffma_bwd_kernel<TI, TO>, smem)) != cudaSuccess) return e; \
     ffma_bwd_kernel<TI, TO><<<grid, NT, smem, stream>>>(a);                    \
+    if (a.splits > 1) ffma_bwd_reduce_kernel<TI, TO><<<rblocks, 256, 0, stream>>>(a); \
   } while (0)
   if (a.z_dtype == SUPCON_BF16) {
     if (dz_dtype == SUPCON_BF16) SUPCON_LAUNCH_BWD(__nv_bfloat16, __nv_bfloat16);

@@ -22,10 +22,23 @@ struct FfmaArgs {
   int n_total, row_offset, n_rows, d;
   int z_dtype, similarity, topk, kcap, mine, vec_ok;
   float tau, alpha, lambda_uni, uni_t;
+  // column splits (ffma_plan): partial records / candidate lists / partial dz in the workspace
+  int splits, col_tiles, rows_pad;
+  float* part;      // [splits][rows_pad][8]
+  float* lv_part;   // [splits][rows_pad][kcap]
+  int* li_part;
+  float* dz_part;   // [splits][rows_pad][d]
+};
+
+struct FfmaPlan {
+  int fwd_splits, bwd_splits, col_tiles, rows_pad, kcap, merge_blocks;
+  size_t off_block_partials, off_part, off_lv, off_li, off_dz, total_bytes;
 };
 
 int ffma_kcap();
-size_t ffma_workspace_bytes(int n_rows);
+FfmaPlan ffma_plan(const supcon_problem_t* p);
+void ffma_bind_plan(FfmaArgs& a, const FfmaPlan& pl, void* workspace, bool backward);
+size_t ffma_workspace_bytes(const supcon_problem_t* p);
 cudaError_t ffma_forward(const FfmaArgs& a, cudaStream_t stream);
 cudaError_t ffma_backward(const FfmaArgs& a, int dz_dtype, cudaStream_t stream);
 cudaError_t ffma_topk_indices(const FfmaArgs& a, int32_t* idx_out, cudaStream_t stream);
