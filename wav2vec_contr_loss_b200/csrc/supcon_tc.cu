@@ -188,34 +188,67 @@ struct RowSums {
 };
 
 constexpr int TC_KCAP = 32;      // in-sweep list capacity per row on the tensor path
-constexpr int LIST_STRIDE = 256; // lists are interleaved over the 256 softmax threads (conflict-free)
+constexpr int LIST_STRIDE = 32;  // list of row (thread) t: lv[t * 32 .. t * 32 + K)  (values), li likewise
 
-// Sorted insert, order (value desc, index asc).  Columns reach a thread in ascending index order and a
-// candidate must be strictly greater than the current K-th value, so ties keep the lower index.
 struct MineState {
   float thr;  // K-th best value once the list is full, -inf before
   int cnt;
 };
-__device__ __noinline__ void mine_insert(float* lv, int* li, int K, MineState& st, float s, int gj) {
-  int p;
-  if (st.cnt < K) p = st.cnt++;
-  else p = K - 1;
-  while (p > 0 && lv[(p - 1) * LIST_STRIDE] < s) {
-    lv[p * LIST_STRIDE] = lv[(p - 1) * LIST_STRIDE];
-    li[p * LIST_STRIDE] = li[(p - 1) * LIST_STRIDE];
-    --p;
+
+// Warp-cooperative sorted insert into the list of lane L's row, order (value desc, index asc).
+// A per-thread insertion would serialise the whole warp behind one lane's dependent shared-memory
+// shifts (rare per row, but 32 rows share a warp); here lane e owns list entry e, the position comes
+// from a ballot and the shift is one parallel step.  Columns reach a row in ascending index order
+// and a candidate must beat the current K-th value strictly, so ties keep the lower index.
+__device__ __forceinline__ void coop_insert(float* wl_v, int* wl_i, int lane, int L, float sL, int gj, int K,
+                                            MineState& ms) {
+  float* rv = wl_v + L * LIST_STRIDE;
+  int* ri = wl_i + L * LIST_STRIDE;
+  const int cntL = __shfl_sync(0xffffffffu, ms.cnt, L);
+  const bool have = lane < cntL;
+  const float ve = have ? rv[lane] : -INFINITY;
+  const int ie = have ? ri[lane] : 0;
+  const int p = __popc(__ballot_sync(0xffffffffu, have && ve >= sL));   // entries that stay ahead
+  __syncwarp();
+  if (have && lane >= p && lane + 1 < K) { rv[lane + 1] = ve; ri[lane + 1] = ie; }
+  if (lane == p && p < K) { rv[p] = sL; ri[p] = gj; }
+  __syncwarp();
+  const int newcnt = min(cntL + 1, K);
+  const float newthr = (newcnt >= K) ? rv[K - 1] : -INFINITY;
+  if (lane == L) { ms.cnt = newcnt; ms.thr = newthr; }
+}
+
+// Hard-negative candidates of one 32-column chunk, handled after the chunk's arithmetic, in column
+// order, re-checked against the row's CURRENT K-th value (the same decisions as an element-by-element
+// scan).  Kept out of line and compact: inlining it 32x per chunk made the hot loop miss the
+// instruction cache (forward 12x slower).  The similarity of a flagged column is re-read from tensor
+// memory (the S buffer is released only after the tile's candidates are done when mining).
+__device__ __noinline__ MineState mine_candidates(int sim, uint32_t taddr_chunk, unsigned anyc, unsigned cmask, int gj0,
+                                                  float* wl_v, int* wl_i, int lane, int K, MineState ms) {
+  while (anyc) {
+    const int e = __ffs(anyc) - 1;
+    anyc &= anyc - 1;
+    const float c = __uint_as_float(ptx::tmem_ld1(taddr_chunk + e));
+    ptx::tmem_ld_wait();
+    const float s = (sim == SUPCON_GEODESIC) ? geodesic_sim_fast(c) : c;
+    unsigned cands = __ballot_sync(0xffffffffu, ((cmask >> e) & 1u) && s > ms.thr);
+    while (cands) {
+      const int L = __ffs(cands) - 1;
+      cands &= cands - 1;
+      coop_insert(wl_v, wl_i, lane, L, __shfl_sync(0xffffffffu, s, L), gj0 + e, K, ms);
+    }
   }
-  lv[p * LIST_STRIDE] = s;
-  li[p * LIST_STRIDE] = gj;
-  st.thr = (st.cnt >= K) ? lv[(K - 1) * LIST_STRIDE] : -INFINITY;
+  return ms;
 }
 
 template <int SIM, bool UNI, bool MINE, bool MASKED>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int gi, int n_total, int lab_r,
                                           float nrm_r, const int32_t* __restrict__ lab_s,
                                           const float* __restrict__ nrm_s, float c1, float c0, float ut2,
-                                          RowSums& st, MineState& ms, float* lv, int* li, int K) {
+                                          RowSums& st, MineState& ms, float* wl_v, int* wl_i, int lane, int K,
+                                          uint32_t taddr_chunk) {
   // lab_s / nrm_s: this chunk's 32 column labels / squared norms in shared memory (broadcast reads)
+  unsigned cmask = 0;   // mining: elements of this chunk that beat the row's K-th value as of the chunk start
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int4 lb = *reinterpret_cast<const int4*>(lab_s + 4 * q);
@@ -242,9 +275,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
         st.sum_pos_s += s;
         if (MINE) st.sum_pos_e += ex;
       }
-      if (MINE) {
-        if (neg && s > ms.thr) mine_insert(lv, li, K, ms, s, gj0 + 4 * q + e);
-      }
+      if (MINE) cmask |= ((neg && s > ms.thr) ? 1u : 0u) << (4 * q + e);
       if (UNI) {
         float w = ex2f(-ut2 * fmaxf(nrm_r + njs[e] - 2.f * c, 0.f));
         if (MASKED) {
@@ -254,6 +285,10 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
         st.wsum += w;
       }
     }
+  }
+  if (MINE) {
+    const unsigned anyc = __reduce_or_sync(0xffffffffu, cmask);
+    if (anyc) ms = mine_candidates(SIM, taddr_chunk, anyc, cmask, gj0, wl_v, wl_i, lane, K, ms);
   }
 }
 
@@ -387,9 +422,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
     const int wg = (warp - 2) >> 2;
     const int lrow = 32 * (warp & 3) + lane;  // TMEM lane == row within the block
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
-    const int tslot = (warp - 2) * 32 + lane;
-    float* lv = reinterpret_cast<float*>(sZJ + STAGES * TILE_BYTES) + tslot;       // [TC_KCAP][256] values
-    int* li = reinterpret_cast<int*>(lv - tslot + TC_KCAP * LIST_STRIDE) + tslot;  // [TC_KCAP][256] indices
+    // top-K lists: [256 rows][32] values then [256 rows][32] indices; this warp's 32 rows start at wl_v / wl_i
+    float* wl_v = reinterpret_cast<float*>(sZJ + STAGES * TILE_BYTES) + (warp - 2) * 32 * LIST_STRIDE;
+    int* wl_i = reinterpret_cast<int*>(sZJ + STAGES * TILE_BYTES + 256 * LIST_STRIDE * 4) + (warp - 2) * 32 * LIST_STRIDE;
     const int K = a.kcap;
     const uint32_t taddr = tmem + lane_addr + TM_S + wg * BN;
     int g = 0;
@@ -421,21 +456,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
         ptx::tmem_ld32(taddr + 64, r2);
         ptx::tmem_ld32(taddr + 96, r3);
         ptx::tmem_ld_wait();
-        ptx::tc_fence_before_sync();
-        ptx::mbar_arrive(&bar_tempty[wg]);   // S_g is free again: the next MMA overlaps the work below
+        if (!MINE) {
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&bar_tempty[wg]);   // S_g is free again: the next MMA overlaps the work below
+        }
         const bool masked = (col0 + BN > a.n_total) || (col0 < rblk0 + TBM && rblk0 < col0 + BN);
         const int32_t* lab_s = lab_ring[slot];
         const float* nrm_s = nrm_ring[UNI ? slot : 0];
         if (masked) {
-          fwd_chunk<SIM, UNI, MINE, true>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-          fwd_chunk<SIM, UNI, MINE, true>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-          fwd_chunk<SIM, UNI, MINE, true>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-          fwd_chunk<SIM, UNI, MINE, true>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+          fwd_chunk<SIM, UNI, MINE, true>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
+          fwd_chunk<SIM, UNI, MINE, true>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
+          fwd_chunk<SIM, UNI, MINE, true>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
+          fwd_chunk<SIM, UNI, MINE, true>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
         } else {
-          fwd_chunk<SIM, UNI, MINE, false>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-          fwd_chunk<SIM, UNI, MINE, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-          fwd_chunk<SIM, UNI, MINE, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
-          fwd_chunk<SIM, UNI, MINE, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, lv, li, K);
+          fwd_chunk<SIM, UNI, MINE, false>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
+          fwd_chunk<SIM, UNI, MINE, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
+          fwd_chunk<SIM, UNI, MINE, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
+          fwd_chunk<SIM, UNI, MINE, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+        }
+        if (MINE) {   // candidates re-read S from tensor memory: release the buffer only now
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&bar_tempty[wg]);
         }
       }
       if (gi < a.row_offset + a.n_rows) {
@@ -446,8 +487,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
         *reinterpret_cast<float4*>(out + 4) = make_float4(st.sum_pos_e, __int_as_float(ms.cnt), 0.f, 0.f);
         if (MINE) {
           for (int e = 0; e < ms.cnt; ++e) {
-            a.topk_v[rec * K + e] = lv[e * LIST_STRIDE];
-            a.topk_i[rec * K + e] = li[e * LIST_STRIDE];
+            a.topk_v[rec * K + e] = wl_v[lane * LIST_STRIDE + e];
+            a.topk_i[rec * K + e] = wl_i[lane * LIST_STRIDE + e];
           }
         }
       }
@@ -462,6 +503,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
 // merge the column splits into row statistics + loss partial sums
 __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishArgs f, float* __restrict__ row_stats) {
   __shared__ double red[5 * 128];
+  __shared__ float mrg_v[TC_KCAP * 128];   // per-thread merge lists, entry-major (conflict-free)
+  __shared__ int mrg_i[TC_KCAP * 128];
   const int lr = blockIdx.x * 128 + threadIdx.x;
   double l_full = 0.0, c_full = 0.0, l_mined = 0.0, c_mined = 0.0, w = 0.0;
   if (lr < a.n_rows) {
@@ -496,8 +539,8 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
       // merge the per-segment top-K lists, each sorted by (value desc, index asc); the full (value, index)
       // comparison makes the result independent of the order in which the segments are visited
       const int K = a.kcap;
-      float mv[TC_KCAP];
-      int mi[TC_KCAP];
+      float* mv = mrg_v + threadIdx.x;   // entry e at mv[e * 128]
+      int* mi = mrg_i + threadIdx.x;
       int cnt = 0;
       for (int ps = 0; ps < 2; ++ps)
         for (int s = slot_lo[ps]; s < slot_lo[ps] + slot_n[ps]; ++s) {
@@ -508,19 +551,19 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
             const int ix = a.topk_i[rec * K + e];
             int p;
             if (cnt < K) p = cnt++;
-            else if (v > mv[K - 1] || (v == mv[K - 1] && ix < mi[K - 1])) p = K - 1;
+            else if (v > mv[(K - 1) * 128] || (v == mv[(K - 1) * 128] && ix < mi[(K - 1) * 128])) p = K - 1;
             else break;   // this list is sorted: nothing further down can enter
-            while (p > 0 && (mv[p - 1] < v || (mv[p - 1] == v && mi[p - 1] > ix))) {
-              mv[p] = mv[p - 1]; mi[p] = mi[p - 1]; --p;
+            while (p > 0 && (mv[(p - 1) * 128] < v || (mv[(p - 1) * 128] == v && mi[(p - 1) * 128] > ix))) {
+              mv[p * 128] = mv[(p - 1) * 128]; mi[p * 128] = mi[(p - 1) * 128]; --p;
             }
-            mv[p] = v; mi[p] = ix;
+            mv[p * 128] = v; mi[p * 128] = ix;
           }
         }
       float sum_top = 0.f;
-      for (int e = 0; e < K; ++e) sum_top += ex2f(fmaf(mv[e], a.c1, a.c0));
+      for (int e = 0; e < K; ++e) sum_top += ex2f(fmaf(mv[e * 128], a.c1, a.c0));
       lse_m = logf(sum_pos_e + sum_top) + a.inv_tau;
-      thr_val = mv[K - 1];
-      thr_idx = mi[K - 1];
+      thr_val = mv[(K - 1) * 128];
+      thr_idx = mi[(K - 1) * 128];
     }
     float* so = row_stats + (int64_t)lr * SUPCON_STATS_STRIDE;
     so[SUPCON_ST_LSE] = lse;
@@ -593,8 +636,8 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw
         // j in pos_i U top_i  /  i in pos_j U top_j, re-derived from the stored thresholds
         const int gj = gj0 + 4 * q + e;
         const bool pos = labs[e] == lab_r;
-        const bool mem_r = pos || s > rm.thr || (s == rm.thr && gj <= rm.thr_idx);
-        const bool mem_c = pos || s > Ts[e] || (s == Ts[e] && gi <= Is[e]);
+        const bool mem_r = pos | (s > rm.thr) | ((s == rm.thr) & (gj <= rm.thr_idx));
+        const bool mem_c = pos | (s > Ts[e]) | ((s == Ts[e]) & (gi <= Is[e]));
         v = fmaf(e0, (mem_r ? rm.Am : 0.f) + (mem_c ? Ams[e] : 0.f), v);
       }
       if (labs[e] == lab_r) v -= B_r + Bs[e];
