@@ -664,7 +664,7 @@ template <int SIM, bool UNI, bool MINE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapJ,
                                                              const __nv_bfloat16* __restrict__ z, TcBwdArgs a) {
   constexpr int BN = 64;
-  constexpr int STAGES = 4;
+  constexpr int STAGES = 6;
   constexpr int RING = STAGES;
   constexpr uint32_t BOXJ_BYTES = BN * 128;            // Z_J boxes: 64 rows x 128 B
   constexpr uint32_t TILEJ_BYTES = NBOX * BOXJ_BYTES;  // 32 KB
@@ -1177,7 +1177,7 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   a.rows_pad = pl.rows_pad; a.sched = pl.bwd_sched;
   a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
   a.scalars = pa.scalars;
-  const size_t smem = 4 * (size_t)NBOX * 64 * 128 + 1024;
+  const size_t smem = 6 * (size_t)NBOX * 64 * 128 + 1024;   // 6 x 32 KB Z_J stages
   const int ctas = pl.bwd_sched.P;
   const bool geo = p->similarity == SUPCON_GEODESIC;
   const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
