@@ -43,6 +43,10 @@ extern "C" {
 #define SUPCON_FLAG_FORCE_EXACT 1u   /* never take the bf16 tensor-core path          */
 #define SUPCON_FLAG_FORCE_TENSOR 2u  /* fail (SUPCON_E_UNSUPPORTED) instead of falling back */
 #define SUPCON_FLAG_NO_SMALL 4u      /* do not use the single-launch small-batch kernel */
+/* test-only: take the tensor path for one direction and the exact path for the other (not valid with
+ * hard-negative mining: the two paths rank by different Gram arithmetic) */
+#define SUPCON_FLAG_DEBUG_TC_FWD_ONLY 8u
+#define SUPCON_FLAG_DEBUG_TC_BWD_ONLY 16u
 
 /* error codes */
 #define SUPCON_E_INVALID (-1)

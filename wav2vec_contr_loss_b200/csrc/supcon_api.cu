@@ -48,8 +48,7 @@ int validate(const supcon_problem_t* p) {
   return 0;
 }
 
-// internal debug flags (tests): take the tensor path for only one direction
-constexpr uint32_t FLAG_TC_FWD_ONLY = 8u, FLAG_TC_BWD_ONLY = 16u;
+constexpr uint32_t FLAG_TC_FWD_ONLY = SUPCON_FLAG_DEBUG_TC_FWD_ONLY, FLAG_TC_BWD_ONLY = SUPCON_FLAG_DEBUG_TC_BWD_ONLY;
 
 bool use_tc(const supcon_problem_t* p, bool backward) {
   if (p->flags & SUPCON_FLAG_FORCE_EXACT) return false;
