@@ -161,6 +161,16 @@ int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int3
 int supcon_debug_tc_tile(const void* z_bf16, int32_t n, int32_t d, int32_t row_i, int32_t row_j,
                          float* s_out, float* o_out, void* stream);
 
+/* Host-only introspection of the tensor path's work distribution (CPU tests, no device work):
+ *   supcon_debug_plan  out[0..11] = {fwd CTAs, fwd column tiles, fwd partial-record slots, bwd CTAs, bwd column
+ *                      tiles, bwd slots, two-phase eligible, own-column-phase CTAs, other-column-phase CTAs,
+ *                      own-column-phase slots, forward (256-row) blocks, backward (128-row) blocks}
+ *   supcon_debug_sched the contiguous unit range of one CTA and the first/last CTA touching a row block for a
+ *                      flattened (row block, column tile) list of `units` = row_blocks * col_tiles entries */
+int supcon_debug_plan(const supcon_problem_t* p, int32_t* out, int32_t n_out);
+int supcon_debug_sched(int32_t col_tiles, int32_t ctas, int64_t units, int32_t cta, int32_t row_block,
+                       int64_t* range_begin, int64_t* range_end, int32_t* first_cta, int32_t* last_cta);
+
 #ifdef __cplusplus
 }
 #endif

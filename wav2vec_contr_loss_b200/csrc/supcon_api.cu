@@ -357,4 +357,23 @@ int supcon_debug_tc_tile(const void* z_bf16, int32_t n, int32_t d, int32_t row_i
   return 0;
 }
 
+int supcon_debug_plan(const supcon_problem_t* p, int32_t* out, int32_t n_out) {
+  if (int rc = validate(p)) return rc;
+  if (!out || n_out < 1) return fail(SUPCON_E_INVALID, "bad arguments to supcon_debug_plan");
+  if (!tc_supported(p)) return fail(SUPCON_E_UNSUPPORTED, "problem does not take the tensor path");
+  return tc_debug_plan(p, out, n_out);
+}
+
+int supcon_debug_sched(int32_t col_tiles, int32_t ctas, int64_t units, int32_t cta, int32_t row_block,
+                       int64_t* range_begin, int64_t* range_end, int32_t* first_cta, int32_t* last_cta) {
+  if (col_tiles < 1 || ctas < 1 || units < ctas || cta < 0 || cta >= ctas || !range_begin || !range_end ||
+      !first_cta || !last_cta)
+    return fail(SUPCON_E_INVALID, "bad arguments to supcon_debug_sched");
+  long long b = 0, e = 0;
+  int f = 0, l = 0;
+  tc_debug_sched(col_tiles, ctas, units, cta, row_block, &b, &e, &f, &l);
+  *range_begin = b; *range_end = e; *first_cta = f; *last_cta = l;
+  return 0;
+}
+
 }  // extern "C"

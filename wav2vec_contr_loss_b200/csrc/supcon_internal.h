@@ -99,6 +99,9 @@ struct TcBwdArgs {
 TcPlan tc_plan(const supcon_problem_t* p);
 bool tc_supported(const supcon_problem_t* p);
 bool tc_two_phase(const supcon_problem_t* p);
+int tc_debug_plan(const supcon_problem_t* p, int32_t* out, int n_out);
+int tc_debug_sched(int T, int P, long long U, int cta, int row_block, long long* range_begin, long long* range_end,
+                   int* first_cta, int* last_cta);
 int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, float* row_stats,
                double* partials, float* loss_out, void* workspace, cudaStream_t stream, const char** err,
                int phase = 0);

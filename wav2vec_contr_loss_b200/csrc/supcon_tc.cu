@@ -1014,6 +1014,27 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   return pl;
 }
 
+// host-side introspection for the CPU tests of the work distribution (no device work)
+int tc_debug_plan(const supcon_problem_t* p, int32_t* out, int n_out) {
+  const TcPlan pl = tc_plan(p);
+  const int32_t v[12] = {pl.fwd_sched.P, pl.fwd_sched.T, pl.fwd_slots, pl.bwd_sched.P, pl.bwd_sched.T, pl.bwd_slots,
+                         pl.two_phase ? 1 : 0, pl.two_phase ? pl.fwd_sched_local.P : 0,
+                         pl.two_phase ? pl.fwd_sched_remote.P : 0, pl.two_phase ? pl.slots_local : 0,
+                         pl.fwd_row_blocks, pl.row_blocks};
+  for (int i = 0; i < n_out && i < 12; ++i) out[i] = v[i];
+  return 0;
+}
+int tc_debug_sched(int T, int P, long long U, int cta, int row_block, long long* range_begin, long long* range_end,
+                   int* first_cta, int* last_cta) {
+  TcSched sc;
+  sc.T = T; sc.P = P; sc.U = U;
+  *range_begin = sched_begin(sc, cta);
+  *range_end = sched_begin(sc, cta + 1);
+  *first_cta = sched_cta_of(sc, (long long)row_block * T);
+  *last_cta = sched_cta_of(sc, (long long)row_block * T + T - 1);
+  return 0;
+}
+
 bool tc_supported(const supcon_problem_t* p) {
   if (p->z_dtype != SUPCON_BF16 || p->d != TD) return false;
   if (!(p->tau >= 0.025f)) return false;
