@@ -150,6 +150,20 @@ int supcon_normalize_forward(const float* x, int32_t n, int32_t d, void* z_out, 
 int supcon_normalize_backward(const void* z, int32_t z_dtype, const float* norms, const void* dz,
                               int32_t dz_dtype, int32_t n, int32_t d, float* dx_out, void* stream);
 
+/* Producer of z: the compression head up to its Linear layer fused with the time mean
+ * (compression_module.py:48-65 + the seq.mean(dim=-1) of stage1_utils.py:122-123).  Because the Linear layer and the
+ * time mean commute, mean_t Linear(x_t) = Linear(mean_t x_t), and what is left of the head is one pass over hs:
+ *   pooled[b][f] = (1/T) sum_t LeakyReLU(Dropout((1/K) sum_k hs[b][k][f][t]))
+ * hs is (batch, layers, feat, frames) fp32 contiguous.  rng_state = device {seed, offset} (two 64-bit words) of the
+ * counter-based dropout mask, or NULL / dropout_p == 0 for eval mode; the backward must be given the same values.
+ * supcon_head_pool_backward writes d loss / d hs (same shape as hs) and is only needed when the encoder trains. */
+int supcon_head_pool_forward(const float* hs, int32_t batch, int32_t layers, int32_t feat, int32_t frames,
+                             float dropout_p, float negative_slope, const uint64_t* rng_state,
+                             float* pooled_out /*[batch][feat]*/, void* stream);
+int supcon_head_pool_backward(const float* hs, int32_t batch, int32_t layers, int32_t feat, int32_t frames,
+                              float dropout_p, float negative_slope, const uint64_t* rng_state,
+                              const float* dpooled /*[batch][feat]*/, float* dhs_out, void* stream);
+
 /* Diagnostics used by the parity tests: hard-negative index sets of the owned
  * rows, recomputed from the statistics (index ascending, -1 padded). */
 int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,

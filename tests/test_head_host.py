@@ -1,0 +1,42 @@
+"""CPU: host side of the fused compression head (wav2vec_contr_loss_b200.head) - parameter names compatible with
+the reference's CompressionModule checkpoints, no CPU path, launch-geometry rules of csrc/supcon_head.cu."""
+import pytest
+import torch
+
+from oracle.ref_loader import load_reference_module, reference_available
+from wav2vec_contr_loss_b200 import FusedCompressionHead, layer_time_pool
+
+
+def test_parameters_are_the_reference_modules():
+    head = FusedCompressionHead(1024, 256, 0.1)
+    assert list(head.state_dict().keys()) == ["mlp3.weight", "mlp3.bias"]     # compression_module.py:30-32
+    assert head.mlp3.weight.shape == (256, 1024) and head.dropout_head.p == 0.1
+    assert head.activation_head.negative_slope == 0.01
+    assert "rng_state" not in head.state_dict() and head.rng_state.dtype == torch.int64
+
+
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container only)")
+def test_loads_a_reference_checkpoint():
+    ref = load_reference_module("compression_module")
+    theirs = ref.CompressionModule(input_dim=48, hidden_dim=12, dropout_rate=0.2)
+    ours = FusedCompressionHead(48, 12, 0.2)
+    missing, unexpected = ours.load_state_dict(theirs.state_dict(), strict=True)
+    assert not missing and not unexpected
+    assert torch.equal(ours.mlp3.weight, theirs.mlp3.weight)
+    assert [n for n, _ in ours.named_parameters()] == [n for n, _ in theirs.named_parameters()]
+
+
+def test_dropout_stream_follows_manual_seed():
+    torch.manual_seed(11)
+    a = FusedCompressionHead(8, 4)
+    torch.manual_seed(12)
+    b = FusedCompressionHead(8, 4)
+    assert a.rng_state.tolist() == [11, 0] and b.rng_state.tolist() == [12, 0]
+
+
+def test_no_cpu_path():
+    head = FusedCompressionHead(8, 4, 0.0)
+    hs = torch.randn(2, 3, 8, 5)
+    for call in (lambda: head(hs), lambda: head.embed(hs), lambda: layer_time_pool(hs)):
+        with pytest.raises((RuntimeError, ValueError, OSError)):
+            call()

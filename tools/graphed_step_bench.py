@@ -47,10 +47,12 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--frames", type=int, default=199)
+    ap.add_argument("--head", choices=("torch", "fused"), default="torch",
+                    help="torch: the reference's op chain; fused: FusedCompressionHead (csrc/supcon_head.cu)")
     args = ap.parse_args()
     from wav2vec_contr_loss_b200 import build
     build.build()
-    from wav2vec_contr_loss_b200 import SupConBinaryLoss
+    from wav2vec_contr_loss_b200 import FusedCompressionHead, SupConBinaryLoss, layer_time_pool
     from wav2vec_contr_loss_b200 import stage1 as S
 
     dev = torch.device("cuda", 0)
@@ -59,10 +61,19 @@ def main():
     hs = torch.randn(B, 25, 1024, args.frames, device=dev)
     y = (torch.arange(B, device=dev) % 2).long()
     loss_fn = SupConBinaryLoss(temperature=0.07, similarity="cosine", uniformity_weight=0.0)
-    out = {"batch": B, "hs_shape": list(hs.shape), "hs_GB": hs.numel() * 4 / 1e9, "iters": args.iters}
+    out = {"batch": B, "hs_shape": list(hs.shape), "hs_GB": hs.numel() * 4 / 1e9, "iters": args.iters,
+           "head": args.head}
+    if args.head == "fused":
+        rng = torch.tensor([1337, 0], dtype=torch.int64, device=dev)
+        with torch.no_grad():
+            t_eval = median_ms(lambda: layer_time_pool(hs, 0.0, 0.01, None), args.iters)
+            t_drop = median_ms(lambda: layer_time_pool(hs, 0.1, 0.01, rng), args.iters)
+        out["head_pool_kernel"] = {"eval_ms": t_eval, "dropout_ms": t_drop,
+                                   "eval_GBps": hs.numel() * 4 / 1e6 / t_eval,
+                                   "dropout_GBps": hs.numel() * 4 / 1e6 / t_drop}
 
     for alpha in (0.0, 0.5):
-        head = LayerMeanHead().to(dev).train()
+        head = (FusedCompressionHead() if args.head == "fused" else LayerMeanHead()).to(dev).train()
         opt = torch.optim.AdamW(head.parameters(), lr=5e-3, weight_decay=3e-3, capturable=True)
 
         def eager_step():

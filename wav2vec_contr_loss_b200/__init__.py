@@ -8,5 +8,6 @@ library (``include/supcon_b200.h``) of hand-written CUDA kernels.
 from .loss import (BCEBinaryLoss, SupConBinaryLoss, SupConMultiClassLoss,  # noqa: F401
                    compute_pos_weight_from_dataset)
 from .functional import l2_normalize, supcon_loss  # noqa: F401
+from .head import FusedCompressionHead, layer_time_pool  # noqa: F401
 
 __version__ = "0.1.0"

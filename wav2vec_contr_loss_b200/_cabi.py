@@ -22,7 +22,8 @@ EXPORTS = (
     "supcon_abi_version", "supcon_last_error", "supcon_workspace_bytes", "supcon_forward_rows",
     "supcon_finalize", "supcon_backward_rows", "supcon_loss_and_grad", "supcon_normalize_forward",
     "supcon_normalize_backward", "supcon_topk_indices", "supcon_debug_tc_tile", "supcon_forward_rows_local",
-    "supcon_forward_rows_remote", "supcon_debug_plan", "supcon_debug_sched",
+    "supcon_forward_rows_remote", "supcon_debug_plan", "supcon_debug_sched", "supcon_head_pool_forward",
+    "supcon_head_pool_backward",
 )
 
 
@@ -88,6 +89,12 @@ def load():
     lib.supcon_debug_sched.restype = c_int32
     lib.supcon_debug_sched.argtypes = [c_int32, c_int32, ctypes.c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                        c_void_p, c_void_p]
+    lib.supcon_head_pool_forward.restype = c_int32
+    lib.supcon_head_pool_forward.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float,
+                                             c_void_p, c_void_p, c_void_p]
+    lib.supcon_head_pool_backward.restype = c_int32
+    lib.supcon_head_pool_backward.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float,
+                                              c_void_p, c_void_p, c_void_p, c_void_p]
     if lib.supcon_abi_version() != 1:
         raise RuntimeError("libsupcon_b200.so ABI version mismatch")
     _lib = lib

@@ -4,6 +4,7 @@
 //   small  single-launch cluster kernel for small batches   (supcon_small.cu)
 //   tc     bf16 tcgen05/TMEM/TMA flash-style kernels         (supcon_tc.cu)
 //   ffma   exact fp32 CUDA-core kernels, any shape           (supcon_ffma.cu)
+// plus the producer of z (supcon_head.cu) and the row normalisation either side of the loss.
 // There is no CPU path: if no CUDA kernel can take the problem the call fails.
 #include <stdarg.h>
 #include <stdio.h>
@@ -329,6 +330,47 @@ int supcon_normalize_backward(const void* z, int32_t z_dtype, const float* norms
   else return fail(SUPCON_E_INVALID, "unknown dtype");
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "normalize_bwd_kernel");
+  return 0;
+}
+
+static int head_pool_check(const float* hs, int32_t batch, int32_t layers, int32_t feat, int32_t frames,
+                           float dropout_p, const void* out, const char* who) {
+  if (!hs || !out) return fail(SUPCON_E_INVALID, "NULL buffer passed to %s", who);
+  if (batch < 1 || layers < 1 || feat < 1 || frames < 1)
+    return fail(SUPCON_E_INVALID, "%s: bad shape (%d, %d, %d, %d)", who, batch, layers, feat, frames);
+  if (batch > 65535) return fail(SUPCON_E_UNSUPPORTED, "%s: batch %d > 65535", who, batch);
+  if (!(dropout_p >= 0.f && dropout_p < 1.f)) return fail(SUPCON_E_INVALID, "%s: dropout_p must be in [0, 1)", who);
+  if (head_pool_rows_per_block(feat, frames) < 1)
+    return fail(SUPCON_E_UNSUPPORTED, "%s: %d frames exceed the 12288 a block can stage", who, frames);
+  return 0;
+}
+
+int supcon_head_pool_forward(const float* hs, int32_t batch, int32_t layers, int32_t feat, int32_t frames,
+                             float dropout_p, float negative_slope, const uint64_t* rng_state, float* pooled_out,
+                             void* stream) {
+  if (int rc = head_pool_check(hs, batch, layers, feat, frames, dropout_p, pooled_out, "supcon_head_pool_forward"))
+    return rc;
+  HeadPoolArgs a{};
+  a.hs = hs; a.pooled = pooled_out; a.rng_state = reinterpret_cast<const unsigned long long*>(rng_state);
+  a.B = batch; a.K = layers; a.F = feat; a.T = frames;
+  a.dropout_p = dropout_p; a.negative_slope = negative_slope;
+  cudaError_t e = head_pool_forward(a, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "head_pool_fwd_kernel");
+  return 0;
+}
+
+int supcon_head_pool_backward(const float* hs, int32_t batch, int32_t layers, int32_t feat, int32_t frames,
+                              float dropout_p, float negative_slope, const uint64_t* rng_state,
+                              const float* dpooled, float* dhs_out, void* stream) {
+  if (int rc = head_pool_check(hs, batch, layers, feat, frames, dropout_p, dhs_out, "supcon_head_pool_backward"))
+    return rc;
+  if (!dpooled) return fail(SUPCON_E_INVALID, "NULL dpooled passed to supcon_head_pool_backward");
+  HeadPoolArgs a{};
+  a.hs = hs; a.pooled = nullptr; a.rng_state = reinterpret_cast<const unsigned long long*>(rng_state);
+  a.B = batch; a.K = layers; a.F = feat; a.T = frames;
+  a.dropout_p = dropout_p; a.negative_slope = negative_slope;
+  cudaError_t e = head_pool_backward(a, dpooled, dhs_out, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "head_pool_bwd_kernel");
   return 0;
 }
 

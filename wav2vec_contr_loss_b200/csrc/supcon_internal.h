@@ -124,6 +124,19 @@ struct SmallArgs {
 bool small_supported(const supcon_problem_t* p, const void* z);
 cudaError_t small_launch(const SmallArgs& a, cudaStream_t stream);
 
+// ---- producer of z: compression head up to the Linear layer, fused with the time mean (supcon_head.cu) ----
+struct HeadPoolArgs {
+  const float* hs;                      // [B][K][F][T]
+  float* pooled;                        // fwd out [B][F]
+  const unsigned long long* rng_state;  // device {seed, offset}; NULL = no dropout
+  int B, K, F, T;
+  float dropout_p, negative_slope;
+  int rows_per_block;                   // filled by the launcher
+};
+int head_pool_rows_per_block(int F, int T);
+cudaError_t head_pool_forward(HeadPoolArgs a, cudaStream_t stream);
+cudaError_t head_pool_backward(HeadPoolArgs a, const float* dpooled, float* dhs, cudaStream_t stream);
+
 // tcgen05 building-block diagnostic (supcon_tc_debug.cu)
 int tc_debug_tile(const void* z_bf16, int n, int d, int row_i, int row_j, float* s_out, float* o_out,
                   cudaStream_t stream, const char** err);

@@ -173,7 +173,8 @@ class GradSync:
 def embed(head, hs: torch.Tensor, normalize: Optional[Callable] = None) -> torch.Tensor:
     """``F.normalize(head(hs).mean(dim=-1), p=2, dim=1)`` of stage1_utils.py:122-123,148-149 with the row
     normalisation on this library's kernel (forward and backward)."""
-    pooled = head(hs).mean(dim=-1)
+    fused = getattr(head, "pooled_embedding", None)          # head.FusedCompressionHead: one pass over hs
+    pooled = fused(hs) if fused is not None else head(hs).mean(dim=-1)
     return (normalize or Fn.l2_normalize)(pooled)
 
 
