@@ -19,7 +19,6 @@ exactly the pooled embedding.  ``embed(hs)`` goes all the way to the normalised 
 comes from a counter-based generator inside the kernel (Bernoulli(1 - p), scaled by 1/(1-p), like ``nn.Dropout``;
 the stream differs from torch's, as it would between two torch versions).  There is no CPU path.
 """
-import ctypes
 
 import torch
 import torch.nn as nn
@@ -70,7 +69,7 @@ class _LayerTimePool(torch.autograd.Function):
         with torch.cuda.device(dev):
             dhs = torch.empty_like(x)
             _cabi.check(lib.supcon_head_pool_backward(Fn._p(x), b, k, f, t, dropout_p, negative_slope,
-                                                      Fn._p(rng) if has_rng else ctypes.c_void_p(0), Fn._p(g),
+                                                      Fn._p(rng) if has_rng else None, Fn._p(g),
                                                       Fn._p(dhs), Fn._stream(dev)),
                         "supcon_head_pool_backward")
         return dhs.to(in_dtype), None, None, None

@@ -41,6 +41,8 @@ class SupConMultiClassLoss(nn.Module):
     """Khosla-style SupCon over arbitrary class ids (reference loss.py:156-210):
     the full-SupCon branch with cosine similarity, no mining, no uniformity."""
 
+    takes_mining_args = False      # forward(z, labels) only: stage1.call_loss drops topk_neg / alpha
+
     def __init__(self, temperature: float = 0.1):
         super().__init__()
         self.tau = temperature

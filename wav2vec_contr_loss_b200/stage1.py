@@ -37,7 +37,8 @@ from torch.utils.data import Sampler
 
 from . import functional as Fn
 
-__all__ = ["alpha_for_epoch", "BalancedBatchSampler", "RunningLoss", "GradSync", "embed", "normalized_supcon_loss",
+__all__ = ["alpha_for_epoch", "BalancedBatchSampler", "RunningLoss", "GradSync", "embed", "call_loss",
+           "normalized_supcon_loss",
            "train_one_epoch", "evaluate", "setup_distributed", "export_embeddings", "GraphedHeadStep"]
 
 
@@ -181,7 +182,15 @@ def embed(head, hs: torch.Tensor, normalize: Optional[Callable] = None) -> torch
 def normalized_supcon_loss(x: torch.Tensor, labels: torch.Tensor, loss_fn, topk_neg: int = 32, alpha: float = 0.0,
                            normalize: Optional[Callable] = None) -> torch.Tensor:
     """normalise + loss in one call: ``x`` are the un-normalised pooled features (N, d)."""
-    return loss_fn((normalize or Fn.l2_normalize)(x), labels, topk_neg=topk_neg, alpha=alpha)
+    return call_loss(loss_fn, (normalize or Fn.l2_normalize)(x), labels, topk_neg, alpha)
+
+
+def call_loss(loss_fn, z, labels, topk_neg: int, alpha: float) -> torch.Tensor:
+    """``loss_fn(z, labels, topk_neg=..., alpha=...)`` (stage1_utils.py:125), or ``loss_fn(z, labels)`` for a loss
+    without mining arguments such as ``SupConMultiClassLoss`` (train_multiclass_con.py:162,210)."""
+    if getattr(loss_fn, "takes_mining_args", True):
+        return loss_fn(z, labels, topk_neg=topk_neg, alpha=alpha)
+    return loss_fn(z, labels)
 
 
 def _to_device(waveforms, labels, device):
@@ -196,27 +205,28 @@ def _check_augment(cfg, augment):
 
 def train_one_epoch(encoder, head, loss_fn, loader, optimizer, device, epoch, cfg, *,
                     normalize: Optional[Callable] = None, augment: Optional[Callable] = None,
-                    grad_sync: Optional[Callable] = None, max_grad_norm: float = 5.0):
+                    grad_sync: Optional[Callable] = None, max_grad_norm: float = 5.0, label_index: int = 1):
     """One training epoch; returns ``(mean loss over steps and ranks, alpha)`` like stage1_utils.py:101-134.
 
     ``loader`` yields ``(waveforms, labels, *rest)``; zero samples are padding (``attention_mask``).  The encoder
     runs without grad unless ``cfg.finetune_encoder``.  ``grad_sync`` (e.g. ``GradSync(head.parameters())``) runs
-    after ``backward`` when the loss is the sharded global-batch loss."""
+    after ``backward`` when the loss is the sharded global-batch loss.  ``label_index`` picks the label column
+    of the batch tuple: 1 = bonafide/spoof, 2 = the multi-class ids of train_multiclass_con.py:147."""
     _check_augment(cfg, augment)
     finetune = bool(cfg.finetune_encoder)
     encoder.train(finetune)
     head.train()
     alpha = alpha_for_epoch(epoch, cfg)
     running = RunningLoss(device)
-    for waveforms, labels, *_ in loader:
-        waveforms, labels = _to_device(waveforms, labels, device)
+    for batch in loader:
+        waveforms, labels = _to_device(batch[0], batch[label_index], device)
         if augment is not None and getattr(cfg, "use_rawboost", False):
             waveforms = augment(waveforms, cfg)
         mask = (waveforms != 0.0).long()
         with torch.set_grad_enabled(finetune):
             hs = encoder(waveforms, attention_mask=mask)
         z = embed(head, hs, normalize)
-        loss = loss_fn(z, labels, topk_neg=cfg.topk_neg, alpha=alpha)
+        loss = call_loss(loss_fn, z, labels, cfg.topk_neg, alpha)
 
         optimizer.zero_grad(set_to_none=True)
         loss.backward()
@@ -229,15 +239,16 @@ def train_one_epoch(encoder, head, loss_fn, loader, optimizer, device, epoch, cf
 
 
 @torch.no_grad()
-def evaluate(encoder, head, loss_fn, loader, device, cfg, *, normalize: Optional[Callable] = None):
+def evaluate(encoder, head, loss_fn, loader, device, cfg, *, normalize: Optional[Callable] = None,
+             label_index: int = 1):
     """Mean loss over a loader with alpha = 0 and no graph (stage1_utils.py:137-153)."""
     encoder.eval()
     head.eval()
     running = RunningLoss(device)
-    for waveforms, labels, *_ in loader:
-        waveforms, labels = _to_device(waveforms, labels, device)
+    for batch in loader:
+        waveforms, labels = _to_device(batch[0], batch[label_index], device)
         hs = encoder(waveforms, attention_mask=(waveforms != 0.0).long())
-        running.add(loss_fn(embed(head, hs, normalize), labels, topk_neg=cfg.topk_neg, alpha=0.0))
+        running.add(call_loss(loss_fn, embed(head, hs, normalize), labels, cfg.topk_neg, 0.0))
     return running.average()
 
 
@@ -337,7 +348,7 @@ class GraphedHeadStep:
 
     def _eager(self, alpha: float) -> torch.Tensor:
         z = embed(self.head, self.hs, self.normalize)
-        loss = self.loss_fn(z, self.labels, topk_neg=self.topk_neg, alpha=alpha)
+        loss = call_loss(self.loss_fn, z, self.labels, self.topk_neg, alpha)
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
         if self.grad_sync is not None:
