@@ -40,3 +40,24 @@ def test_no_cpu_path():
     for call in (lambda: head(hs), lambda: head.embed(hs), lambda: layer_time_pool(hs)):
         with pytest.raises((RuntimeError, ValueError, OSError)):
             call()
+
+
+def test_c_abi_argument_validation_without_gpu(lib_built):
+    """every rejected call returns before any CUDA work, so this runs on the CPU-only box"""
+    import ctypes
+    from wav2vec_contr_loss_b200 import _cabi
+    lib = _cabi.load()
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    fwd, bwd = lib.supcon_head_pool_forward, lib.supcon_head_pool_backward
+    assert fwd(None, 2, 3, 4, 5, 0.0, 0.01, None, p, None) == -1 and b"NULL" in lib.supcon_last_error()
+    assert fwd(p, 2, 3, 4, 5, 0.0, 0.01, None, None, None) == -1
+    assert fwd(p, 0, 3, 4, 5, 0.0, 0.01, None, p, None) == -1 and b"bad shape" in lib.supcon_last_error()
+    assert fwd(p, 2, 3, 4, 5, 1.0, 0.01, None, p, None) == -1 and b"dropout_p" in lib.supcon_last_error()
+    assert fwd(p, 2, 3, 4, 5, -0.1, 0.01, None, p, None) == -1
+    assert fwd(p, 70000, 3, 4, 5, 0.0, 0.01, None, p, None) == -2 and b"65535" in lib.supcon_last_error()
+    assert fwd(p, 2, 3, 4, 12289, 0.0, 0.01, None, p, None) == -2 and b"frames" in lib.supcon_last_error()
+    assert bwd(p, 2, 3, 4, 5, 0.0, 0.01, None, None, p, None) == -1 and b"dpooled" in lib.supcon_last_error()
+    assert bwd(p, 2, 3, 4, 5, 0.0, 0.01, None, p, None, None) == -1
+    with pytest.raises(RuntimeError, match="supcon_head_pool_forward failed"):
+        _cabi.check(fwd(None, 2, 3, 4, 5, 0.0, 0.01, None, p, None), "supcon_head_pool_forward")
