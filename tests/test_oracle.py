@@ -139,3 +139,23 @@ def test_oracle_against_live_reference(sim, tau, lam, k, alpha, classes):
     r = O.closed_form(z, y, temperature=tau, similarity=sim, uniformity_weight=lam, topk_neg=k, alpha=alpha)
     assert r["loss"] == pytest.approx(float(loss), rel=1e-12)
     assert torch.allclose(r["dz"], z.grad, rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("sim", ["cosine", "geodesic"])
+def test_duplicate_rows_with_uniformity_against_live_reference(sim):
+    """exact duplicate rows: zero pairwise distances inside the uniformity term (pdist's backward is 0 there,
+    loss.py:91-93) and ties at the K-th hard negative; the loss value is tie-order invariant."""
+    ref = load_reference_module("loss")
+    x, y = O.make_inputs(64, 16, "ties", seed=11)
+    z = F.normalize(x.double(), dim=1)
+    assert int(((z[:, None, :] - z[None, :, :]).abs().sum(-1) == 0).sum()) > 64      # real duplicates present
+    zr = z.clone().requires_grad_(True)
+    loss = ref.SupConBinaryLoss(0.1, sim, 0.3, 2.0)(zr, y, topk_neg=5, alpha=0.0)
+    loss.backward()
+    r = O.closed_form(z, y, temperature=0.1, similarity=sim, uniformity_weight=0.3, topk_neg=5, alpha=0.0)
+    assert r["loss"] == pytest.approx(float(loss), rel=1e-12)
+    assert torch.allclose(r["dz"], zr.grad, rtol=1e-9, atol=1e-13)
+    mined = ref.SupConBinaryLoss(0.1, sim, 0.3, 2.0)(z, y, topk_neg=5, alpha=1.0)
+    r1 = O.closed_form(z, y, temperature=0.1, similarity=sim, uniformity_weight=0.3, topk_neg=5, alpha=1.0)
+    assert r1["loss"] == pytest.approx(float(mined), rel=1e-12)
