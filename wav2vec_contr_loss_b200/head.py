@@ -18,6 +18,9 @@ the sequence ALREADY averaged over time, shape (B, D, 1): the unchanged caller's
 exactly the pooled embedding.  ``embed(hs)`` goes all the way to the normalised z.  In train mode the dropout mask
 comes from a counter-based generator inside the kernel (Bernoulli(1 - p), scaled by 1/(1-p), like ``nn.Dropout``;
 the stream differs from torch's, as it would between two torch versions).  There is no CPU path.
+
+One process per GPU: do not wrap this module in ``nn.DataParallel`` for training - replicas are rebuilt from the
+master copy every step and their buffer updates are discarded, so the dropout offset would never advance.
 """
 
 import torch
