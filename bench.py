@@ -12,9 +12,11 @@ cosine SupCon, tau 0.07, N = 65536, d = 256, bf16 z / fp32-or-bf16 dz.  With
 (strong scaling at fixed N): all-gather z/labels -> row-block forward ->
 all-reduce partial sums -> all-gather row stats -> row-block backward.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU
-algorithm (the oracle's per-anchor port; /root/reference does not exist on the
-GPU box) on a bounded sample of the same workload.
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU
+implementation -- the UNMODIFIED loss.py behind F.normalize, from the verbatim
+copies oracle/build_ref.py stages under oracle/_ref (they ship with the gpurun
+snapshot; /root/reference does not exist on the GPU box) -- on a bounded sample
+of the same workload, and adds the N x threads table of BASELINE.md section 3.
 """
 import argparse
 import json
@@ -49,6 +51,8 @@ def parse():
     ap.add_argument("--alpha", type=float, default=0.0)
     ap.add_argument("--cpu-sample-n", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-table", action="store_true",
+                    help="--impl reference: skip the N x threads table of BASELINE.md section 3")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: N fixed (BASELINE configs[3] as named); weak: per-GPU pair count fixed, "
@@ -138,44 +142,104 @@ def synth(n, d, dtype, seed=1337):
     return z, y
 
 
-def cpu_port_step(z, y, args):
-    """One fwd+bwd of the reference algorithm (oracle port of loss.py) on the CPU. Returns seconds."""
-    import torch
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_reference_loss(args):
+    """The CPU implementation that stands for the reference: the UNMODIFIED loss.py when it is reachable
+    (oracle/_ref staged by oracle/build_ref.py, or /root/reference in the build container; kind "reference"),
+    else the oracle's per-anchor port of it (kind "port").  Returns (callable(z, y) -> loss, kind, description)."""
+    from oracle import ref_loader as R
+    if R.reference_available():
+        mod = R.load_reference_module("loss")
+        fn = mod.SupConBinaryLoss(temperature=args.tau, similarity=args.similarity,
+                                  uniformity_weight=args.lambda_uni, uniformity_t=2.0)
+        return (lambda z, y: fn(z, y, topk_neg=args.topk, alpha=args.alpha)), "reference", \
+            f"unmodified loss.py:110-153 ({R.reference_kind()})"
     from oracle import supcon_oracle as O
-    zz = z.float().clone().requires_grad_(True)
+    return (lambda z, y: O.anchor_loop_loss(z, y, temperature=args.tau, similarity=args.similarity,
+                                            uniformity_weight=args.lambda_uni, uniformity_t=2.0,
+                                            topk_neg=args.topk, alpha=args.alpha)), "port", \
+        "per-anchor loop port of loss.py (oracle/supcon_oracle.py)"
+
+
+def cpu_ref_step(loss_fn, x, y):
+    """One fwd+bwd as the reference's caller runs it (stage1_utils.py:123-128): F.normalize -> loss -> backward.
+    Returns (fwd seconds, bwd seconds)."""
+    import torch
+    xx = x.clone().requires_grad_(True)
     t0 = time.perf_counter()
-    loss = O.anchor_loop_loss(zz, y, temperature=args.tau, similarity=args.similarity,
-                              uniformity_weight=args.lambda_uni, uniformity_t=2.0, topk_neg=args.topk,
-                              alpha=args.alpha)
+    loss = loss_fn(torch.nn.functional.normalize(xx, p=2, dim=1), y)
+    t1 = time.perf_counter()
     loss.backward()
-    return time.perf_counter() - t0
+    return t1 - t0, time.perf_counter() - t1
+
+
+def cpu_reference_table(args, loss_fn, budget_s=150.0):
+    """literal loss at N in {64, 256, 1024, 2048}, 1 thread and all cores, fwd / bwd split,
+    median of the timed runs after one warm-up; rows are dropped once the time budget is spent."""
+    import torch
+    cores = os.cpu_count() or 1
+    rows, t_start = [], time.perf_counter()
+    for n, reps in ((64, 5), (256, 5), (1024, 3), (2048, 1)):
+        g = torch.Generator().manual_seed(1337)
+        x = torch.randn(n, args.d, generator=g)
+        y = torch.zeros(n, dtype=torch.int64)
+        y[torch.randperm(n, generator=g)[: n // 2]] = 1
+        for threads in (1, cores):
+            if time.perf_counter() - t_start > budget_s:
+                return rows
+            torch.set_num_threads(threads)
+            if n <= 1024:
+                cpu_ref_step(loss_fn, x, y)
+            ts = [cpu_ref_step(loss_fn, x, y) for _ in range(reps)]
+            f, b = statistics.median(t[0] for t in ts), statistics.median(t[1] for t in ts)
+            rows.append({"N": n, "threads": threads, "fwd_ms": round(1e3 * f, 2), "bwd_ms": round(1e3 * b, 2),
+                         "pairs_per_s": n * n / (f + b), "runs": reps, "warmup": 1 if n <= 1024 else 0})
+    torch.set_num_threads(cores)
+    return rows
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation, all host threads, bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path (unmodified loss.py behind
+    F.normalize) on the box's host cores, all threads, each step one fwd+bwd over a bounded sample (the first
+    cpu_sample_n rows/columns) of the workload; plus the BASELINE.md table (N, threads, fwd/bwd split)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    loss_fn, kind, what = cpu_reference_loss(args)
     n = min(args.cpu_sample_n, args.n)
     z, y = synth(n, args.d, torch.float32)
     for _ in range(args.warmup):
-        cpu_port_step(z, y, args)
-    times = [cpu_port_step(z, y, args) for _ in range(args.steps)]
-    t = sum(times) / len(times)
+        cpu_ref_step(loss_fn, z, y)
+    times = [cpu_ref_step(loss_fn, z, y) for _ in range(args.steps)]
+    t = sum(a + b for a, b in times) / len(times)
     value = n * n / t
+    sample = (f"first {n} rows/cols of the workload (N^2 = {n * n} pairs each step), fp32, F.normalize + {what}, "
+              f"{cores} threads, fwd {1e3 * statistics.median(a for a, _ in times):.0f} ms + bwd "
+              f"{1e3 * statistics.median(b for _, b in times):.0f} ms, torch {torch.__version__}, CPU {cpu_model()}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, extra={"sample_n": n}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"first {n} rows/cols of the workload (N^2 pairs each step), fp32, "
-                                   f"per-anchor loop port of loss.py, torch {torch.__version__}"},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_model": cpu_model(), "host_cores": cores,
     }
+    if not args.no_ref_table:
+        line["cpu_table"] = cpu_reference_table(args, loss_fn)
     print(json.dumps(line), flush=True)
 
 
@@ -519,14 +583,16 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
+            loss_fn, kind, what = cpu_reference_loss(args)
             ns = min(args.cpu_sample_n, n)
-            zc, yc = z_host[:ns].float(), y_host[:ns]
-            cpu_port_step(zc, yc, args)
-            tcs = [cpu_port_step(zc, yc, args) for _ in range(3)]
+            g = torch.Generator().manual_seed(1337)
+            xc, yc = torch.randn(ns, d, generator=g), y_host[:ns]
+            cpu_ref_step(loss_fn, xc, yc)
+            tcs = [sum(cpu_ref_step(loss_fn, xc, yc)) for _ in range(3)]
             tc = statistics.median(tcs)
-            line["cpu_baseline"] = {"value": ns * ns / tc, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"first {ns} rows/cols of the workload, fp32, per-anchor loop port "
-                                              f"of loss.py, median of 3, {tc:.2f} s per fwd+bwd"}
+            line["cpu_baseline"] = {"value": ns * ns / tc, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{ns} rows/cols (N^2 pairs per fwd+bwd), fp32, F.normalize + {what}, "
+                                              f"median of 3, {tc:.2f} s per fwd+bwd, CPU {cpu_model()}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tearing the process group down while captured NCCL graphs are alive can block; every rank has
