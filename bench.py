@@ -9,8 +9,11 @@ unit-norm embeddings (value = N^2 / t).  Default workload = BASELINE.json
 configs[3], the largest single-GPU configuration the metric is quoted on:
 cosine SupCon, tau 0.07, N = 65536, d = 256, bf16 z / fp32-or-bf16 dz.  With
 --gpus R > 1 (launched by torchrun) the N rows are sharded over the ranks
-(strong scaling at fixed N): all-gather z/labels -> row-block forward ->
-all-reduce partial sums -> all-gather row stats -> row-block backward.
+(strong scaling at fixed N): all-gather z/labels overlapped with the forward over
+the rank's own columns -> the other columns -> all-gather of row statistics and
+partial sums overlapped with the backward over the own columns -> the rest.
+The timed call is the drop-in module itself (SupConBinaryLoss / ShardedSupConLoss
+called as stage1_utils.py:125-128 calls the reference's) + autograd.
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU
 implementation -- the UNMODIFIED loss.py behind F.normalize, from the verbatim
@@ -61,6 +64,8 @@ def parse():
                     help="loss: the SupCon hot path (default, BASELINE configs[3]); stage1: one Stage-1 training step "
                          "around it (BASELINE configs[4]) reporting the loss's share of the step")
     ap.add_argument("--stage1-batch", type=int, default=64)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the N = 64 / 1024 / mined side measurements (one GPU only)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -374,8 +379,9 @@ def main():
     import torch.distributed as dist
     from wav2vec_contr_loss_b200 import build as _build
     _build.build()
+    from wav2vec_contr_loss_b200 import SupConBinaryLoss, _cabi
     from wav2vec_contr_loss_b200 import functional as Fn
-    from wav2vec_contr_loss_b200.distributed import _CudaKernels, exchange_stats, gather_and_forward, gather_inputs
+    from wav2vec_contr_loss_b200.distributed import ShardedSupConLoss, exchange_stats, gather_inputs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -401,33 +407,30 @@ def main():
     z_local = zl_host.to(dev)
     y_local = yl_host.to(dev)
     sim_id = Fn.similarity_id(args.similarity)
+    flags = args.flags | _cabi.FLAG_UNIT_ROWS          # synth() L2-normalises the rows
     kw = dict(tau=args.tau, similarity=sim_id, lambda_uni=args.lambda_uni, uni_t=2.0, topk=args.topk,
-              alpha=args.alpha, flags=args.flags)
+              alpha=args.alpha, flags=flags)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # The timed step IS the drop-in boundary: the loss module called like stage1_utils.py:125-128 calls the
+    # reference's -- loss = loss_fn(z, labels, topk_neg=..., alpha=...); loss.backward() -- on one GPU
+    # SupConBinaryLoss, on several ShardedSupConLoss (same signature, rows of the global batch per rank).
+    cls = ShardedSupConLoss if world > 1 else SupConBinaryLoss
+    loss_fn = cls(temperature=args.tau, similarity=args.similarity, uniformity_weight=args.lambda_uni, uniformity_t=2.0)
+    loss_fn.kernel_flags = args.flags
+    loss_fn.assume_unit_rows = True
+    # kernels of libsupcon_b200.so per step on the tensor path.  One GPU: prep_fwd, label_table, tc_fwd, merge,
+    # prep_bwd, tc_bwd, reduce.  Several ranks: forward in two phases (prep + label_table + tc_fwd twice, merge),
+    # finalize_sets, backward in two phases (prep_bwd + tc_bwd twice), reduce.
+    launches_per_step = 7 if world == 1 else 14
     launches = {"count": 0}
 
     def step(z_loc, y_loc):
-        """fwd + bwd through the C-ABI wrappers; returns (loss, dz_local)."""
-        if world > 1:
-            # all-gather overlapped with the forward over the rank's own columns (distributed.gather_and_forward)
-            z_all, y_all, prob, stats, partials = gather_and_forward(
-                z_loc, y_loc, lambda nt, dd, ro, nr: Fn.make_problem(nt, dd, Fn._dtype_id(z_loc), row_offset=ro,
-                                                                     n_rows=nr, **kw), None, _CudaKernels)
-            loss = None
-        else:
-            z_all, y_all = z_loc, y_loc
-            prob = Fn.make_problem(n, d, Fn._dtype_id(z_all), row_offset=0, n_rows=n, **kw)
-            stats, partials, loss = Fn.forward_rows(z_all, y_all, prob, want_loss=True)
-        if world > 1:
-            stats_all = exchange_stats(partials, stats)
-            loss = Fn.finalize(prob, partials)
-        else:
-            stats_all = stats
-        dz = Fn.backward_rows(z_all, y_all, stats_all, partials, None, prob, out_dtype=tdtype)
-        # kernels of libsupcon_b200.so per step on the tensor path: prep_fwd, label_table, tc_fwd, merge, prep_bwd,
-        # tc_bwd, reduce; with several ranks the forward runs in two phases (prep + label_table + tc_fwd twice) and a
-        # finalize kernel turns the exchanged partial sums into the loss
-        launches["count"] += 7 + (4 if world > 1 else 0)
+        """fwd + bwd through the module and autograd; returns (loss, d loss / d z_local)."""
+        z = z_loc.detach().requires_grad_(True)
+        loss = loss_fn(z, y_loc, topk_neg=args.topk, alpha=args.alpha)
+        (dz,) = torch.autograd.grad(loss, z)
+        launches["count"] += launches_per_step
         return loss, dz
 
     class Stepper:
@@ -466,6 +469,17 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step(z_local, y_local)
     barrier()
+
+    # ---- host-inclusive time of the same call issued eagerly from Python (both figures) ----
+    def eager_ms(fn, reps):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0) / reps
+    eager_step_ms = eager_ms(lambda: step(z_local, y_local), min(args.steps, 10))
+
     resident = Stepper(lambda: step(z_local, y_local))
 
     def e2e_step():
@@ -517,8 +531,8 @@ def main():
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = float(t2)
 
-    # ---- per-kernel durations for the roofline: forward-only and backward-only CUDA graphs, CUDA events on
-    #      the launching stream (graph replay keeps host launch gaps out of the kernel time) ----
+    # ---- per-kernel durations for the roofline: forward-only and backward-only CUDA graphs over this rank's
+    #      row block (direct C-ABI wrappers), CUDA events on the launching stream ----
     prob_t = Fn.make_problem(n, d, Fn._dtype_id(z_local), row_offset=rank * n_local, n_rows=n_local, **kw)
     if world > 1:
         z_all_t, y_all_t = gather_inputs(z_local, y_local)
@@ -534,10 +548,11 @@ def main():
     bwd_only = Stepper(lambda: Fn.backward_rows(z_all_t, y_all_t, stats_all_t, partials_t, None, prob_t, out_dtype=tdtype))
     reps = min(args.steps, 10)
 
-    def time_graph(stepper):
+    def time_graph(stepper, reps=reps, do_flush=True):
         tot = 0.0
         for _ in range(reps):
-            flush.zero_()
+            if do_flush:
+                flush.zero_()
             s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s_.record(); stepper(); e_.record()
             torch.cuda.synchronize()
@@ -550,6 +565,36 @@ def main():
     launches["count"] = n_before
     barrier()
 
+    # ---- other configurations of BASELINE.json through the same module (one GPU only; reported, not the metric) ----
+    extras = None
+    if world == 1 and not args.no_extras:
+        def module_case(nn_, dtype, similarity, lam, topk, alpha, reps_):
+            zc, yc = synth(nn_, d, dtype)
+            zc, yc = zc.to(dev), yc.to(dev)
+            fn_ = SupConBinaryLoss(temperature=args.tau, similarity=similarity, uniformity_weight=lam, uniformity_t=2.0)
+            fn_.assume_unit_rows = True
+
+            def one():
+                zz = zc.detach().requires_grad_(True)
+                ls = fn_(zz, yc, topk_neg=topk, alpha=alpha)
+                torch.autograd.grad(ls, zz)
+                return ls
+            for _ in range(3):
+                one()
+            host_ms = eager_ms(one, reps_)
+            dev_ms = time_graph(Stepper(one), reps_, do_flush=False)
+            return {"device_us": round(1e3 * dev_ms, 2), "host_inclusive_us": round(1e3 * host_ms, 2)}
+        extras = {
+            "n64_fwd_bwd_us": module_case(64, torch.float32, "cosine", 0.0, 15, 0.0, 50),               # configs[0]
+            "n64_geodesic_uniformity_us": module_case(64, torch.float32, "geodesic", 0.05, 15, 0.0, 50),  # configs[1]
+            "n1024_mined_f32_us": module_case(1024, torch.float32, "cosine", 0.0, 15, 0.5, 20),           # configs[2]
+            "n1024_mined_bf16_us": module_case(1024, torch.bfloat16, "cosine", 0.0, 15, 0.5, 20),
+            "n65536_mined_bf16_us": module_case(65536, torch.bfloat16, "cosine", 0.0, 15, 0.5, 5),
+            "note": "fwd+bwd through SupConBinaryLoss + autograd; device_us = one CUDA-graph replay (CUDA events), "
+                    "host_inclusive_us = eager Python call, wall clock incl. launch overhead",
+        }
+        launches["count"] = n_before
+
     if rank == 0:
         pk = peaks()
         pairs = float(n) * float(n)
@@ -558,16 +603,23 @@ def main():
         bwd_tflops = pairs / world * flop_per_pair_bwd / (bwd_ms * 1e-3) / 1e12
         fwd_tflops = pairs / world * flop_per_pair_fwd / (fwd_ms * 1e-3) / 1e12
         total_tflops = pairs * (flop_per_pair_bwd + flop_per_pair_fwd) / (ms_per_step * 1e-3) / 1e12
+        cfg = workload_config(args)
+        cfg["api"] = (f"{cls.__name__}(temperature, similarity, ...)(z, labels, topk_neg, alpha) + autograd backward "
+                      f"(the reference's call, stage1_utils.py:125-128); assume_unit_rows=True")
         line = {
             "metric": METRIC, "value": pairs / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args),
+            "config": cfg,
             "clocks": clocks,
             "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(zl_host.numel() * zl_host.element_size() + yl_host.numel() * 4),
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+                    "dz": f"device-resident ({args.dtype}: autograd returns the gradient in z's dtype; it feeds the "
+                          f"normalisation backward on the device, only the scalar loss goes back to the host)"},
+            "boundary": {"graph_replay_ms": ms_per_step, "eager_host_inclusive_ms": eager_step_ms,
+                         "note": "same module call; eager = issued from Python every step, wall clock with a final sync"},
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor", "kernel": "tc_bwd_kernel + its prep/reduce (recompute S, dz = (G+G^T) z)",
                          "achieved": bwd_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
@@ -580,15 +632,17 @@ def main():
             "step_tflops": total_tflops, "step_frac_of_bf16_peak": total_tflops / pk["tflops"] / world,
             "loss": float(loss),
         }
+        if extras is not None:
+            line["extras"] = extras
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            loss_fn, kind, what = cpu_reference_loss(args)
+            loss_ref, kind, what = cpu_reference_loss(args)
             ns = min(args.cpu_sample_n, n)
             g = torch.Generator().manual_seed(1337)
             xc, yc = torch.randn(ns, d, generator=g), y_host[:ns]
-            cpu_ref_step(loss_fn, xc, yc)
-            tcs = [sum(cpu_ref_step(loss_fn, xc, yc)) for _ in range(3)]
+            cpu_ref_step(loss_ref, xc, yc)
+            tcs = [sum(cpu_ref_step(loss_ref, xc, yc)) for _ in range(3)]
             tc = statistics.median(tcs)
             line["cpu_baseline"] = {"value": ns * ns / tc, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"{ns} rows/cols (N^2 pairs per fwd+bwd), fp32, F.normalize + {what}, "

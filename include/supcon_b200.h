@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SUPCON_ABI_VERSION 1
+#define SUPCON_ABI_VERSION 2
 
 /* element type of z / dz buffers */
 #define SUPCON_F32 0
@@ -43,10 +43,15 @@ extern "C" {
 #define SUPCON_FLAG_FORCE_EXACT 1u   /* never take the bf16 tensor-core path          */
 #define SUPCON_FLAG_FORCE_TENSOR 2u  /* fail (SUPCON_E_UNSUPPORTED) instead of falling back */
 #define SUPCON_FLAG_NO_SMALL 4u      /* do not use the single-launch small-batch kernel */
-/* test-only: take the tensor path for one direction and the exact path for the other (not valid with
+/* diagnostics: take the tensor path for one direction and the exact path for the other (not valid with
  * hard-negative mining: the two paths rank by different Gram arithmetic) */
 #define SUPCON_FLAG_DEBUG_TC_FWD_ONLY 8u
 #define SUPCON_FLAG_DEBUG_TC_BWD_ONLY 16u
+/* Caller's promise that the rows of z are L2-normalised (what every caller of the reference passes,
+ * stage1_utils.py:123): |z_i|^2 <= 1 + 2^-6.  Cosine similarity only reaches the bf16 tensor-core path under
+ * this promise (its exponentials use one fixed maximum); without it z is taken as given on the exact path.
+ * The promise is CHECKED on the device: max_i |z_i|^2 > tau / 0.025 makes the loss and dz NaN. */
+#define SUPCON_FLAG_UNIT_ROWS 32u
 
 /* error codes */
 #define SUPCON_E_INVALID (-1)
@@ -73,6 +78,11 @@ extern "C" {
 #define SUPCON_P_SUM_MINED 2
 #define SUPCON_P_CNT_MINED 3
 #define SUPCON_P_SUM_W 4
+/* tensor path only (0 elsewhere); identical on every rank, so never summed across ranks: */
+#define SUPCON_P_GCNT_FULL 5  /* |A_f| of the GLOBAL batch, derived from the gathered labels alone */
+#define SUPCON_P_GCNT_MINED 6 /* |A_m| likewise                                                     */
+#define SUPCON_P_FIXMAX 7     /* fixed maximum M the exponentials were taken against, exp((s - M)/tau):
+                                 1 for unit rows, max_j |z_j|^2 otherwise, NaN = promise broken      */
 
 typedef struct supcon_problem {
   int32_t n_total;    /* N: columns = global batch                                   */
@@ -125,6 +135,13 @@ int supcon_forward_rows_remote(const supcon_problem_t* p, const void* z_all, con
 int supcon_finalize(const supcon_problem_t* p, const double* partials_global, float* loss_out,
                     void* stream);
 
+/* Rank-ordered sum of the partial sums of `n_sets` ranks + the scalar loss in ONE launch (what the sharded
+ * path runs after all-gathering every rank's partials): slots 0..4 are summed in set order (deterministic,
+ * identical on all ranks), slots SUPCON_P_GCNT_* / SUPCON_P_FIXMAX are copied from set 0.
+ *   partial_sets [n_sets][SUPCON_N_PARTIALS]   partials_out [SUPCON_N_PARTIALS]   loss_out optional */
+int supcon_finalize_sets(const supcon_problem_t* p, const double* partial_sets, int32_t n_sets,
+                         double* partials_out, float* loss_out, void* stream);
+
 /* Backward for the owned rows (replaces autograd through loss.py:96-153):
  *   dz_i = grad_out * sum_j (G_ij + G_ji) z_j (+ uniformity), recomputing the
  *   similarity tiles; needs the statistics of ALL rows and the global partials.
@@ -135,6 +152,24 @@ int supcon_backward_rows(const supcon_problem_t* p, const void* z_all, const int
                          const float* stats_all, const double* partials_global,
                          const float* grad_out, void* dz_out, int32_t dz_dtype, void* workspace,
                          size_t workspace_bytes, void* stream);
+
+/* Two-phase form of supcon_backward_rows for ranks that overlap the exchange of row statistics with compute
+ * (the symmetric formulation dz_i = sum_j (G_ij + G_ji) z_j needs the statistics of column j):
+ *   _local  sweeps only the columns this rank owns, which need nothing but the rank's OWN statistics
+ *           (stats_local [n_rows][STRIDE]) and its own forward partials (the global anchor counts in
+ *           SUPCON_P_GCNT_* come from the gathered labels), and leaves partial dz records in the workspace;
+ *           grad_out is not needed yet, so this can be issued right after the forward;
+ *   _remote sweeps all other columns with everyone's statistics and the global partial sums, adds both
+ *           phases, scales by grad_out and writes dz_out exactly as supcon_backward_rows would.
+ * Both calls take the SAME workspace.  When the problem is not eligible (exact path, unaligned row block,
+ * uniformity term: its coefficient needs the global sum) _local does nothing and _remote runs everything. */
+int supcon_backward_rows_local(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                               const float* stats_local, const double* partials_local, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int supcon_backward_rows_remote(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                                const float* stats_all, const double* partials_global, const float* grad_out,
+                                void* dz_out, int32_t dz_dtype, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* Whole batch on one GPU: loss and (if dz_out != NULL) d loss / d z in as few
  * launches as the shape allows (one for small batches).  row_stats/partials
@@ -168,22 +203,6 @@ int supcon_head_pool_backward(const float* hs, int32_t batch, int32_t layers, in
  * rows, recomputed from the statistics (index ascending, -1 padded). */
 int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
                         const float* row_stats, int32_t* idx_out /*[n_rows][topk]*/, void* stream);
-
-/* Diagnostic for the tcgen05/TMA building blocks (tests only): for 128-row blocks
- * I = row_i.., J = row_j.. of a bf16 matrix z [n][256] writes S = Z_I Z_J^T
- * ([128][128] fp32) and O = bf16(S) Z_J ([128][256] fp32). */
-int supcon_debug_tc_tile(const void* z_bf16, int32_t n, int32_t d, int32_t row_i, int32_t row_j,
-                         float* s_out, float* o_out, void* stream);
-
-/* Host-only introspection of the tensor path's work distribution (CPU tests, no device work):
- *   supcon_debug_plan  out[0..11] = {fwd CTAs, fwd column tiles, fwd partial-record slots, bwd CTAs, bwd column
- *                      tiles, bwd slots, two-phase eligible, own-column-phase CTAs, other-column-phase CTAs,
- *                      own-column-phase slots, forward (256-row) blocks, backward (128-row) blocks}
- *   supcon_debug_sched the contiguous unit range of one CTA and the first/last CTA touching a row block for a
- *                      flattened (row block, column tile) list of `units` = row_blocks * col_tiles entries */
-int supcon_debug_plan(const supcon_problem_t* p, int32_t* out, int32_t n_out);
-int supcon_debug_sched(int32_t col_tiles, int32_t ctas, int64_t units, int32_t cta, int32_t row_block,
-                       int64_t* range_begin, int64_t* range_end, int32_t* first_cta, int32_t* last_cta);
 
 #ifdef __cplusplus
 }

@@ -8,12 +8,13 @@ from wav2vec_contr_loss_b200.loss import SupConBinaryLoss
 
 
 def kernel_loss_and_grad(z_cpu, y_cpu, *, tau, similarity, lam=0.0, t=2.0, topk=32, alpha=0.0,
-                         dtype=torch.float32, device="cuda:0", flags=0, grad_scale=1.0):
+                         dtype=torch.float32, device="cuda:0", flags=0, grad_scale=1.0, unit_rows=None):
     """Through the public module + autograd. Returns (loss float, dz fp64 cpu)."""
     z = z_cpu.to(device=device, dtype=dtype).requires_grad_(True)
     y = y_cpu.to(device)
     mod = SupConBinaryLoss(tau, similarity, lam, t)
     mod.kernel_flags = flags
+    mod.assume_unit_rows = unit_rows
     loss = mod(z, y, topk_neg=topk, alpha=alpha)
     if loss.requires_grad:
         (grad_scale * loss).backward()
@@ -45,6 +46,7 @@ def kernel_stats(z_cpu, y_cpu, *, tau, similarity, lam=0.0, t=2.0, topk=32, alph
     stats, partials, loss = Fn.forward_rows(z, y, prob, want_loss=whole)
     # index sets are re-derived with the exact fp32 Gram: only meaningful for statistics of the exact paths
     uses_tc = (dtype == torch.bfloat16 and z.size(1) == 256 and z.size(0) >= 256 and tau >= 0.025
-               and not (flags & 1) and (alpha == 0 or topk <= 32))
+               and not (flags & 1) and (alpha == 0 or topk <= 32)
+               and (similarity == "geodesic" or (flags & (2 | 32))))
     idx = Fn.topk_indices(z, y, stats, prob) if (topk >= 1 and not uses_tc) else None
     return dict(z=z, y=y, prob=prob, stats=stats, partials=partials, loss=loss, idx=idx)

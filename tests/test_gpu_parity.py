@@ -75,7 +75,7 @@ def test_bf16_inputs(cuda_device, sim):
     x, y = O.make_inputs(512, 256, "iso")
     zb = F.normalize(x, dim=1).to(torch.bfloat16)
     kw = dict(tau=0.07, similarity=sim, lam=0.05, topk=15, alpha=0.5)
-    loss, dz = G.kernel_loss_and_grad(zb, y, dtype=torch.bfloat16, **kw)
+    loss, dz = G.kernel_loss_and_grad(zb, y, dtype=torch.bfloat16, unit_rows=True, **kw)
     ref = G.oracle_for(zb.float(), y, **kw)      # oracle semantics for bf16: loss.py on z_bf16.float()
     assert loss == pytest.approx(ref["loss"], rel=TOL_BF16)
     assert G.rel_err(dz, ref["dz"]) < 2 * TOL_BF16     # dz itself is rounded to bf16 on return
@@ -295,11 +295,11 @@ def test_tensor_core_path_bf16(cuda_device, n, kind, classes, sim, tau, lam, fla
 
 
 def test_tensor_core_path_through_module(cuda_device):
-    """bf16 z through the drop-in class takes the tensor path by default; grad_out scaling."""
+    """bf16 z with L2-normalised rows (promised) through the drop-in class takes the tensor path; grad_out scaling."""
     x, y = O.make_inputs(1024, 256, "iso")
     zb = F.normalize(x, dim=1).to(torch.bfloat16)
     loss, dz = G.kernel_loss_and_grad(zb, y, tau=0.07, similarity="cosine", topk=15, alpha=0.0,
-                                      dtype=torch.bfloat16, grad_scale=3.0)
+                                      dtype=torch.bfloat16, grad_scale=3.0, unit_rows=True)
     ref = G.oracle_for(zb.float(), y, tau=0.07, similarity="cosine", topk=15, alpha=0.0)
     assert loss == pytest.approx(ref["loss"], rel=TOL_BF16)
     assert G.rel_err(dz, ref["dz"]) < 2 * TOL_BF16      # dz additionally rounded to bf16 by autograd
@@ -429,8 +429,10 @@ def test_sharded_loss_single_rank_nccl(cuda_device):
             z1 = F.normalize(x, dim=1).to(cuda_device).to(dtype).requires_grad_(True)
             z2 = z1.detach().clone().requires_grad_(True)
             yy = y.to(cuda_device)
-            a = ShardedSupConLoss(0.07, "cosine", 0.05)(z1, yy, topk_neg=15, alpha=0.0)
-            b = SupConBinaryLoss(0.07, "cosine", 0.05)(z2, yy, topk_neg=15, alpha=0.0)
+            ma, mb = ShardedSupConLoss(0.07, "cosine", 0.05), SupConBinaryLoss(0.07, "cosine", 0.05)
+            ma.assume_unit_rows = mb.assume_unit_rows = True      # bf16: tensor path
+            a = ma(z1, yy, topk_neg=15, alpha=0.0)
+            b = mb(z2, yy, topk_neg=15, alpha=0.0)
             (2.0 * a).backward(); (2.0 * b).backward()
             assert float(a) == pytest.approx(float(b), rel=1e-6)
             assert G.rel_err(z1.grad.float().cpu(), z2.grad.float().cpu()) < 1e-5

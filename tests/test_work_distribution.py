@@ -5,6 +5,7 @@ import random
 
 import pytest
 
+import debug_lib
 from wav2vec_contr_loss_b200 import _cabi
 from wav2vec_contr_loss_b200.functional import make_problem
 
@@ -18,7 +19,7 @@ def _sched(lib, T, P, U, cta, rb):
 
 
 def test_cta_ranges_partition_the_unit_list(lib_built):
-    lib = _cabi.load()
+    lib = debug_lib.load()
     rng = random.Random(0)
     for _ in range(40):
         row_blocks, T = rng.randint(1, 40), rng.randint(1, 70)
@@ -41,12 +42,12 @@ def test_cta_ranges_partition_the_unit_list(lib_built):
 @pytest.mark.parametrize("n,row_offset,n_rows", [(65536, 0, 65536), (65536, 8192, 8192), (4096, 0, 4096),
                                                   (1000, 0, 1000), (16384, 4096, 4096), (2048, 512, 768)])
 def test_plan_slots_bound_every_row_block(lib_built, n, row_offset, n_rows):
-    lib = _cabi.load()
+    lib = debug_lib.load()
     prob = make_problem(n, 256, _cabi.BF16, tau=0.07, similarity=_cabi.COSINE, topk=15, alpha=0.0,
-                        row_offset=row_offset, n_rows=n_rows)
-    out = (ctypes.c_int32 * 12)()
-    assert lib.supcon_debug_plan(ctypes.byref(prob), out, 12) == 0
-    fP, fT, fslots, bP, bT, bslots, two_phase, lP, rP, lslots, frb, brb = list(out)
+                        row_offset=row_offset, n_rows=n_rows, flags=_cabi.FLAG_UNIT_ROWS)
+    out = (ctypes.c_int32 * 16)()
+    assert lib.supcon_debug_plan(ctypes.byref(prob), out, 16) == 0
+    fP, fT, fslots, bP, bT, bslots, two_phase, lP, rP, lslots, frb, brb, blP, brP, blslots, blT = list(out)
     assert fT == (n + 127) // 128 and bT == (n + 63) // 64
     assert frb == ((n_rows + 127) // 128 + 1) // 2 and brb == (n_rows + 127) // 128
     assert 1 <= fP <= frb * fT and 1 <= bP <= brb * bT
@@ -56,12 +57,25 @@ def test_plan_slots_bound_every_row_block(lib_built, n, row_offset, n_rows):
     assert two_phase == int(n_rows < n and row_offset % 128 == 0 and n_rows % 128 == 0)
     if two_phase:
         assert lP >= 1 and rP >= 1 and lslots >= 1 and fslots >= lslots + 1
+        # backward: the own-column window in 64-column tiles; both phases' slots fit the reserved partial records
+        assert blT == n_rows // 64 and blP >= 1 and brP >= 1 and blslots >= 1 and bslots >= blslots + 1
+        worst_l = max(_sched(lib, blT, blP, brb * blT, 0, rb)[3] - _sched(lib, blT, blP, brb * blT, 0, rb)[2] + 1
+                      for rb in range(brb))
+        rT = bT - blT
+        worst_r = max(_sched(lib, rT, brP, brb * rT, 0, rb)[3] - _sched(lib, rT, brP, brb * rT, 0, rb)[2] + 1
+                      for rb in range(brb))
+        assert worst_l <= blslots and worst_l + worst_r <= bslots
 
 
 def test_plan_rejects_problems_off_the_tensor_path(lib_built):
-    lib = _cabi.load()
+    lib = debug_lib.load()
     out = (ctypes.c_int32 * 12)()
     prob = make_problem(4096, 256, _cabi.F32, tau=0.07, similarity=_cabi.COSINE)
     assert lib.supcon_debug_plan(ctypes.byref(prob), out, 12) == -2
-    prob = make_problem(4096, 128, _cabi.BF16, tau=0.07, similarity=_cabi.COSINE)
+    prob = make_problem(4096, 128, _cabi.BF16, tau=0.07, similarity=_cabi.COSINE, flags=_cabi.FLAG_UNIT_ROWS)
     assert lib.supcon_debug_plan(ctypes.byref(prob), out, 12) == -2
+    # cosine without the caller's unit-rows promise: z is taken as given on the exact path
+    prob = make_problem(4096, 256, _cabi.BF16, tau=0.07, similarity=_cabi.COSINE)
+    assert lib.supcon_debug_plan(ctypes.byref(prob), out, 12) == -2
+    prob = make_problem(4096, 256, _cabi.BF16, tau=0.07, similarity=_cabi.GEODESIC)
+    assert lib.supcon_debug_plan(ctypes.byref(prob), out, 12) == 0

@@ -66,7 +66,7 @@ def time_case(n, d, dtype, sim, tau, lam, k, alpha, flags, iters=20):
     z = F.normalize(x, dim=1).to(dev).to(dtype)
     yl = Fn.canonical_labels(y.to(dev), n)
     prob = Fn.make_problem(n, d, Fn._dtype_id(z), tau=tau, similarity=Fn.similarity_id(sim), lambda_uni=lam,
-                           topk=k, alpha=alpha, flags=flags)
+                           topk=k, alpha=alpha, flags=flags | 32)   # 32: rows are L2-normalised above
 
     def step():
         stats, partials, loss = Fn.forward_rows(z, yl, prob, want_loss=True)

@@ -11,7 +11,7 @@ for n in (1024, 4096, 16384, 65536):
     z = torch.nn.functional.normalize(torch.randn(n, 256, generator=g), dim=1).to(dev).to(torch.bfloat16)
     y = (torch.rand(n, generator=g) < 0.5).to(torch.int32).to(dev)
     for alpha, k in ((0.0, 15), (0.5, 15), (0.5, 32)):
-        prob = Fn.make_problem(n, 256, 1, tau=0.07, similarity=0, topk=k, alpha=alpha)
+        prob = Fn.make_problem(n, 256, 1, tau=0.07, similarity=0, topk=k, alpha=alpha, flags=32)
         def fwd(): return Fn.forward_rows(z, y, prob, want_loss=True)
         stats, partials, loss = fwd()
         def bwd(): return Fn.backward_rows(z, y, stats, partials, None, prob, out_dtype=torch.bfloat16)

@@ -12,7 +12,7 @@ dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(1337)
 z = torch.nn.functional.normalize(torch.randn(n, 256, generator=g), dim=1).to(dev).to(torch.bfloat16)
 y = (torch.rand(n, generator=g) < 0.5).to(torch.int32).to(dev)
-prob = Fn.make_problem(n, 256, 1, tau=0.07, similarity=Fn.similarity_id(sim), topk=15, alpha=0.0)
+prob = Fn.make_problem(n, 256, 1, tau=0.07, similarity=Fn.similarity_id(sim), topk=15, alpha=0.0, flags=32)
 for _ in range(steps):
     stats, partials, loss = Fn.forward_rows(z, y, prob, want_loss=True)
     dz = Fn.backward_rows(z, y, stats, partials, None, prob, out_dtype=torch.bfloat16)

@@ -14,8 +14,8 @@ z = torch.nn.functional.normalize(torch.randn(n, 256, generator=g), dim=1).to(de
 y = (torch.rand(n, generator=g) < 0.5).to(torch.int32).to(dev)
 for R in ranks:
     nl = n // R
-    prob = Fn.make_problem(n, 256, 1, tau=0.07, similarity=0, topk=15, alpha=0.0, row_offset=0, n_rows=nl)
-    whole = Fn.make_problem(n, 256, 1, tau=0.07, similarity=0, topk=15, alpha=0.0)
+    prob = Fn.make_problem(n, 256, 1, tau=0.07, similarity=0, topk=15, alpha=0.0, row_offset=0, n_rows=nl, flags=32)
+    whole = Fn.make_problem(n, 256, 1, tau=0.07, similarity=0, topk=15, alpha=0.0, flags=32)
     stats_all = torch.zeros(n, 8, device=dev)
     for _ in range(3):
         stats, partials, _ = Fn.forward_rows(z, y, prob, want_loss=False)

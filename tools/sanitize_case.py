@@ -11,7 +11,7 @@ def run(n, d, dtype, sim, lam, k, alpha, row_offset=0, n_rows=None, two_phase=Fa
     z = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).to(dev).to(dtype)
     y = torch.randint(0, 3, (n,), generator=g).to(torch.int32).to(dev)
     prob = Fn.make_problem(n, d, Fn._dtype_id(z), tau=0.07, similarity=Fn.similarity_id(sim), lambda_uni=lam, topk=k,
-                           alpha=alpha, row_offset=row_offset, n_rows=n_rows)
+                           alpha=alpha, row_offset=row_offset, n_rows=n_rows, flags=32)
     if two_phase:
         ws = Fn.forward_rows_local(z, y, prob)
         stats, partials = Fn.forward_rows_remote(z, y, prob, ws)

@@ -71,7 +71,7 @@ if args.perf:
         x, y = O.make_inputs(n, 256, "iso")
         z = F.normalize(x, dim=1).to(dev).to(bf16)
         yl = Fn.canonical_labels(y.to(dev), n)
-        prob = Fn.make_problem(n, 256, 1, tau=0.07, similarity=0, topk=15, alpha=0.0)
+        prob = Fn.make_problem(n, 256, 1, tau=0.07, similarity=0, topk=15, alpha=0.0, flags=32)
         for _ in range(3):
             stats, partials, loss = Fn.forward_rows(z, yl, prob, want_loss=True)
             dz = Fn.backward_rows(z, yl, stats, partials, None, prob, out_dtype=bf16)

@@ -3,11 +3,12 @@
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
-from wav2vec_contr_loss_b200 import _cabi
+import debug_lib
 from wav2vec_contr_loss_b200.functional import _p, _stream
 
-lib = _cabi.load()
+lib = debug_lib.load()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 n = 512
@@ -16,7 +17,7 @@ TS = 1 << 24
 for (ri, rj) in [(0, 0), (128, 256), (384, 128), (448, 64), (TS + 0, 0), (TS + 128, 256), (TS + 448, 64)]:
     s = torch.full((128, 128), float("nan"), device=dev)
     o = torch.full((128, 256), float("nan"), device=dev)
-    _cabi.check(lib.supcon_debug_tc_tile(_p(z), n, 256, ri, rj, _p(s), _p(o), _stream(dev)), "debug")
+    debug_lib.check(lib.supcon_debug_tc_tile(_p(z), n, 256, ri, rj, _p(s), _p(o), _stream(dev)), "debug")
     torch.cuda.synchronize()
     mode = "TS" if ri >= TS else "SS"
     ri = ri % TS

@@ -4,10 +4,11 @@ threshold-based hard-negative membership test on the tensor path)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
-from wav2vec_contr_loss_b200 import _cabi
+import debug_lib
 from wav2vec_contr_loss_b200.functional import _p, _stream
-lib = _cabi.load(); dev = torch.device("cuda:0")
+lib = debug_lib.load(); dev = torch.device("cuda:0")
 torch.manual_seed(1)
 n = 512
 z = torch.nn.functional.normalize(torch.randn(n, 256), dim=1).to(dev).to(torch.bfloat16)
@@ -15,7 +16,7 @@ z[300] = z[7]; z[301] = z[7]      # exact duplicates -> exact ties
 TS = 1 << 24
 def tile(ri, rj, ts):
     s = torch.empty(128, 128, device=dev); o = torch.empty(128, 256, device=dev)
-    _cabi.check(lib.supcon_debug_tc_tile(_p(z), n, 256, ri + (TS if ts else 0), rj, _p(s), _p(o), _stream(dev)), "dbg")
+    debug_lib.check(lib.supcon_debug_tc_tile(_p(z), n, 256, ri + (TS if ts else 0), rj, _p(s), _p(o), _stream(dev)), "dbg")
     torch.cuda.synchronize(); return s
 for ts in (False, True):
     a = tile(0, 128, ts); b = tile(128, 0, ts)

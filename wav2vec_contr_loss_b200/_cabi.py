@@ -14,16 +14,19 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 F32, BF16 = 0, 1
 COSINE, GEODESIC = 0, 1
 FLAG_FORCE_EXACT, FLAG_FORCE_TENSOR, FLAG_NO_SMALL = 1, 2, 4
+FLAG_UNIT_ROWS = 32
 STATS_STRIDE = 8
 N_PARTIALS = 8
+P_SUM_FULL, P_CNT_FULL, P_SUM_MINED, P_CNT_MINED, P_SUM_W, P_GCNT_FULL, P_GCNT_MINED, P_FIXMAX = range(8)
+ABI_VERSION = 2
 ST_LSE, ST_LSE_M, ST_NPOS, ST_NNEG, ST_THR_VAL, ST_THR_IDX, ST_WSUM, ST_POS_MEAN = range(8)
 
 EXPORTS = (
     "supcon_abi_version", "supcon_last_error", "supcon_workspace_bytes", "supcon_forward_rows",
     "supcon_finalize", "supcon_backward_rows", "supcon_loss_and_grad", "supcon_normalize_forward",
-    "supcon_normalize_backward", "supcon_topk_indices", "supcon_debug_tc_tile", "supcon_forward_rows_local",
-    "supcon_forward_rows_remote", "supcon_debug_plan", "supcon_debug_sched", "supcon_head_pool_forward",
-    "supcon_head_pool_backward",
+    "supcon_normalize_backward", "supcon_topk_indices", "supcon_forward_rows_local",
+    "supcon_forward_rows_remote", "supcon_head_pool_forward", "supcon_head_pool_backward",
+    "supcon_finalize_sets", "supcon_backward_rows_local", "supcon_backward_rows_remote",
 )
 
 
@@ -82,20 +85,20 @@ def load():
                                               c_int32, c_void_p, c_void_p]
     lib.supcon_topk_indices.restype = c_int32
     lib.supcon_topk_indices.argtypes = [P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
-    lib.supcon_debug_tc_tile.restype = c_int32
-    lib.supcon_debug_tc_tile.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
-    lib.supcon_debug_plan.restype = c_int32
-    lib.supcon_debug_plan.argtypes = [P, c_void_p, c_int32]
-    lib.supcon_debug_sched.restype = c_int32
-    lib.supcon_debug_sched.argtypes = [c_int32, c_int32, ctypes.c_int64, c_int32, c_int32, c_void_p, c_void_p,
-                                       c_void_p, c_void_p]
+    lib.supcon_finalize_sets.restype = c_int32
+    lib.supcon_finalize_sets.argtypes = [P, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.supcon_backward_rows_local.restype = c_int32
+    lib.supcon_backward_rows_local.argtypes = [P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.supcon_backward_rows_remote.restype = c_int32
+    lib.supcon_backward_rows_remote.argtypes = [P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_int32, c_void_p, c_size_t, c_void_p]
     lib.supcon_head_pool_forward.restype = c_int32
     lib.supcon_head_pool_forward.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float,
                                              c_void_p, c_void_p, c_void_p]
     lib.supcon_head_pool_backward.restype = c_int32
     lib.supcon_head_pool_backward.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float,
                                               c_void_p, c_void_p, c_void_p, c_void_p]
-    if lib.supcon_abi_version() != 1:
+    if lib.supcon_abi_version() != ABI_VERSION:
         raise RuntimeError("libsupcon_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1,10 +1,12 @@
-"""Build libsupcon_b200.so in-tree with nvcc for sm_100a.
+"""Build libsupcon_b200.so (+ the test-only libsupcon_b200_test.so) in-tree with nvcc for sm_100a.
 
     python -m wav2vec_contr_loss_b200.build [--force] [--verbose]
 
-The library is a plain C-ABI shared object (include/supcon_b200.h); it links
+libsupcon_b200.so is the product: a plain C-ABI shared object (include/supcon_b200.h); it links
 the static CUDA runtime only, so it loads on a machine without a GPU driver
-(the CPU-side tests check its exported symbols there).
+(the CPU-side tests check its exported symbols there).  libsupcon_b200_test.so is the same objects
+plus the diagnostics of csrc/supcon_debug.h (tcgen05 one-tile kernels, plan introspection); only
+tests/ and tools/ load it.
 """
 import hashlib
 import os
@@ -17,6 +19,8 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsupcon_b200.so")
+TEST_LIB_PATH = os.path.join(LIB_DIR, "libsupcon_b200_test.so")
+TEST_ONLY_SOURCES = ("supcon_tc_debug.cu", "supcon_debug_api.cu")
 STAMP = os.path.join(LIB_DIR, "libsupcon_b200.stamp")
 
 NVCC_FLAGS = [
@@ -53,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile (if stale) and return the path of the shared library."""
     os.makedirs(LIB_DIR, exist_ok=True)
     digest = _digest()
-    if not force and os.path.isfile(LIB_PATH) and os.path.isfile(STAMP):
+    if not force and os.path.isfile(LIB_PATH) and os.path.isfile(TEST_LIB_PATH) and os.path.isfile(STAMP):
         with open(STAMP) as fh:
             if fh.read().strip() == digest:
                 return LIB_PATH
@@ -79,12 +83,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libsupcon_b200.so")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs,
-            "-cudart", "static"]
-    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        print(r.stdout, file=sys.stderr)
-        raise RuntimeError("link failed for libsupcon_b200.so")
+    test_objs = {os.path.join(LIB_DIR, f[:-3] + ".o") for f in TEST_ONLY_SOURCES}
+    for out_path, members in ((LIB_PATH, [o for o in objs if o not in test_objs]), (TEST_LIB_PATH, objs)):
+        link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_path, *members,
+                "-cudart", "static"]
+        r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            print(r.stdout, file=sys.stderr)
+            raise RuntimeError(f"link failed for {os.path.basename(out_path)}")
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB_PATH

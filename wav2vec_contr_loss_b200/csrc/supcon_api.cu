@@ -113,6 +113,23 @@ __global__ void finalize_kernel(const double* pg, float* loss_out, int n_total, 
     *loss_out = global_coef(pg, n_total, tau, alpha, lambda_uni, uni_t).loss;
 }
 
+// sums the per-rank partial sums in rank order (deterministic, identical on every rank) and writes the loss.
+// Slots SUPCON_P_GCNT_* / SUPCON_P_FIXMAX are global quantities every rank derived identically: copied, not summed.
+__global__ void finalize_sets_kernel(const double* sets, int n_sets, double* partials_out, float* loss_out,
+                                     int n_total, float tau, float alpha, float lambda_uni, float uni_t) {
+  __shared__ double pg[SUPCON_N_PARTIALS];
+  const int k = threadIdx.x;
+  if (k < SUPCON_N_PARTIALS) {
+    double s = sets[k];
+    if (k <= SUPCON_P_SUM_W)
+      for (int r = 1; r < n_sets; ++r) s += sets[(int64_t)r * SUPCON_N_PARTIALS + k];
+    pg[k] = s;
+    partials_out[k] = s;
+  }
+  __syncthreads();
+  if (k == 0 && loss_out) *loss_out = global_coef(pg, n_total, tau, alpha, lambda_uni, uni_t).loss;
+}
+
 // ---- row L2 normalisation (stage1_utils.py:123,149): one warp per row ----
 template <typename TO>
 __global__ void normalize_fwd_kernel(const float* __restrict__ x, int n, int d, TO* __restrict__ z,
@@ -175,7 +192,7 @@ int supcon_forward_rows(const supcon_problem_t* p, const void* z_all, const int3
   if (workspace_bytes < workspace_need(p))
     return fail(SUPCON_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, workspace_need(p));
   if ((p->flags & SUPCON_FLAG_FORCE_TENSOR) && !tc_supported(p))
-    return fail(SUPCON_E_UNSUPPORTED, "tensor-core path needs bf16 z, d == 256, tau >= 0.025, N >= 256, no mining");
+    return fail(SUPCON_E_UNSUPPORTED, "tensor-core path needs bf16 z, d == 256, tau >= 0.025, N >= 256, top-K <= 32");
   if (loss_out && (p->row_offset != 0 || p->n_rows != p->n_total))
     return fail(SUPCON_E_INVALID, "loss_out needs a rank that owns every row; use supcon_finalize");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -240,6 +257,55 @@ int supcon_finalize(const supcon_problem_t* p, const double* partials_global, fl
       partials_global, loss_out, p->n_total, p->tau, p->alpha, p->lambda_uni, p->uni_t);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "finalize_kernel");
+  return 0;
+}
+
+int supcon_finalize_sets(const supcon_problem_t* p, const double* partial_sets, int32_t n_sets,
+                         double* partials_out, float* loss_out, void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!partial_sets || !partials_out || n_sets < 1)
+    return fail(SUPCON_E_INVALID, "bad arguments to supcon_finalize_sets");
+  finalize_sets_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial_sets, n_sets, partials_out, loss_out, p->n_total, p->tau, p->alpha, p->lambda_uni, p->uni_t);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "finalize_sets_kernel");
+  return 0;
+}
+
+int supcon_backward_rows_local(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                               const float* stats_local, const double* partials_local, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!(use_tc(p, true) && use_tc(p, false) && tc_bwd_two_phase(p))) return 0;   // _remote does everything
+  if (!z_all || !labels_all || !stats_local || !partials_local || !workspace)
+    return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_backward_rows_local");
+  if (workspace_bytes < workspace_need(p))
+    return fail(SUPCON_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, workspace_need(p));
+  const char* err = "";
+  int rc = tc_backward(p, z_all, labels_all, stats_local, partials_local, nullptr, nullptr, SUPCON_F32, workspace,
+                       reinterpret_cast<cudaStream_t>(stream), &err, 1);
+  if (rc) return fail(rc, "tc_backward(local columns): %s", err);
+  return 0;
+}
+
+int supcon_backward_rows_remote(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
+                                const float* stats_all, const double* partials_global, const float* grad_out,
+                                void* dz_out, int32_t dz_dtype, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!(use_tc(p, true) && use_tc(p, false) && tc_bwd_two_phase(p)))
+    return supcon_backward_rows(p, z_all, labels_all, stats_all, partials_global, grad_out, dz_out, dz_dtype,
+                                workspace, workspace_bytes, stream);
+  if (!z_all || !labels_all || !stats_all || !partials_global || !dz_out || !workspace)
+    return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_backward_rows_remote");
+  if (dz_dtype != SUPCON_F32 && dz_dtype != SUPCON_BF16)
+    return fail(SUPCON_E_INVALID, "unknown dz_dtype %d", dz_dtype);
+  if (workspace_bytes < workspace_need(p))
+    return fail(SUPCON_E_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, workspace_need(p));
+  const char* err = "";
+  int rc = tc_backward(p, z_all, labels_all, stats_all, partials_global, grad_out, dz_out, dz_dtype, workspace,
+                       reinterpret_cast<cudaStream_t>(stream), &err, 2);
+  if (rc) return fail(rc, "tc_backward(remote columns): %s", err);
   return 0;
 }
 
@@ -387,34 +453,6 @@ int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int3
   a.row_stats = const_cast<float*>(row_stats);
   cudaError_t e = ffma_topk_indices(a, idx_out, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "ffma_topk_indices");
-  return 0;
-}
-
-int supcon_debug_tc_tile(const void* z_bf16, int32_t n, int32_t d, int32_t row_i, int32_t row_j, float* s_out,
-                         float* o_out, void* stream) {
-  if (!z_bf16 || !s_out || !o_out) return fail(SUPCON_E_INVALID, "NULL buffer passed to supcon_debug_tc_tile");
-  const char* err = "";
-  int rc = tc_debug_tile(z_bf16, n, d, row_i, row_j, s_out, o_out, reinterpret_cast<cudaStream_t>(stream), &err);
-  if (rc) return fail(rc, "supcon_debug_tc_tile: %s", err);
-  return 0;
-}
-
-int supcon_debug_plan(const supcon_problem_t* p, int32_t* out, int32_t n_out) {
-  if (int rc = validate(p)) return rc;
-  if (!out || n_out < 1) return fail(SUPCON_E_INVALID, "bad arguments to supcon_debug_plan");
-  if (!tc_supported(p)) return fail(SUPCON_E_UNSUPPORTED, "problem does not take the tensor path");
-  return tc_debug_plan(p, out, n_out);
-}
-
-int supcon_debug_sched(int32_t col_tiles, int32_t ctas, int64_t units, int32_t cta, int32_t row_block,
-                       int64_t* range_begin, int64_t* range_end, int32_t* first_cta, int32_t* last_cta) {
-  if (col_tiles < 1 || ctas < 1 || units < ctas || cta < 0 || cta >= ctas || !range_begin || !range_end ||
-      !first_cta || !last_cta)
-    return fail(SUPCON_E_INVALID, "bad arguments to supcon_debug_sched");
-  long long b = 0, e = 0;
-  int f = 0, l = 0;
-  tc_debug_sched(col_tiles, ctas, units, cta, row_block, &b, &e, &f, &l);
-  *range_begin = b; *range_end = e; *first_cta = f; *last_cta = l;
   return 0;
 }
 

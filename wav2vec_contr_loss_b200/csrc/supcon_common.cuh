@@ -48,10 +48,13 @@ struct GlobalCoef {
   float loss;     // the scalar loss
 };
 
+// use_label_counts: take |A_f|, |A_m| from the label-derived GLOBAL counts (SUPCON_P_GCNT_*) that the tensor
+// path's forward leaves in a rank's own partials, so coefficients are known before any exchange.
 __device__ __forceinline__ GlobalCoef global_coef(const double* pg, int n_total, float tau, float alpha,
-                                                  float lambda_uni, float uni_t) {
+                                                  float lambda_uni, float uni_t, bool use_label_counts = false) {
   GlobalCoef g;
-  double cnt_f = pg[SUPCON_P_CNT_FULL], cnt_m = pg[SUPCON_P_CNT_MINED];
+  double cnt_f = pg[use_label_counts ? SUPCON_P_GCNT_FULL : SUPCON_P_CNT_FULL];
+  double cnt_m = pg[use_label_counts ? SUPCON_P_GCNT_MINED : SUPCON_P_CNT_MINED];
   double main_loss = 0.0, wf = 0.0, wm = 0.0;
   if (cnt_f > 0.0) {
     double full = pg[SUPCON_P_SUM_FULL] / cnt_f;
@@ -92,11 +95,15 @@ struct FinishArgs {
   float tau, alpha, lambda_uni, uni_t;
 };
 
-__device__ inline void block_partials_and_finish(const FinishArgs& a, const double* red, int rows) {
+// NV = number of per-row values reduced from `red` ([NV][rows] doubles); slots NV..7 of the block record are 0.
+// `fixmax` (tensor path only) is stored in partials[SUPCON_P_FIXMAX] by the last block; other paths pass 0.
+template <int NV = 5>
+__device__ inline void block_partials_and_finish(const FinishArgs& a, const double* red, int rows,
+                                                 double fixmax = 0.0) {
   __shared__ int is_last;
   const int tid = threadIdx.x;
   double* bp = a.block_partials + (int64_t)blockIdx.x * SUPCON_N_PARTIALS;
-  if (tid < 5) {
+  if (tid < NV) {
     double s = 0.0;
     for (int r = 0; r < rows; ++r) s += red[tid * rows + r];
     bp[tid] = s;
@@ -116,7 +123,7 @@ __device__ inline void block_partials_and_finish(const FinishArgs& a, const doub
     double s = 0.0;
     for (unsigned b = 0; b < gridDim.x; ++b)
       s += *((volatile double*)(a.block_partials + (int64_t)b * SUPCON_N_PARTIALS + tid));
-    a.partials[tid] = s;
+    a.partials[tid] = (tid == SUPCON_P_FIXMAX) ? fixmax : s;
   }
   __syncthreads();
   if (tid == 0) {

@@ -52,8 +52,10 @@ struct TcSched {   // flattened (row block, column tile) work list cut into P co
 struct TcPlan {
   TcSched fwd_sched, bwd_sched;
   TcSched fwd_sched_local, fwd_sched_remote;   // two-phase forward (own columns first, then the others)
+  TcSched bwd_sched_local, bwd_sched_remote;   // two-phase backward, likewise (64-column tiles)
   bool two_phase;
-  int local_ct0, local_cts, slots_local;
+  int local_ct0, local_cts, slots_local;       // forward: own-column window in 128-column tiles
+  int bwd_local_ct0, bwd_local_cts, bwd_slots_local;   // backward: the same window in 64-column tiles
   int n_pad, rows_pad, row_blocks, fwd_row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_slots, bwd_slots, merge_blocks;
   size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
       off_scalars, off_hkeys, off_hcounts, off_topk_v, off_topk_i, off_part, total_bytes;
@@ -65,6 +67,7 @@ struct TcFwdArgs {
   const unsigned long long* hkeys;   // label -> class size table (tc_prep_fwd_kernel)
   const int* hcounts;
   uint32_t hmask;
+  const unsigned* nrm2_max;          // bits of max_j |z_j|^2 over the columns swept so far (workspace header)
   float* part;       // [slots][rows_pad][8]
   float* topk_v;     // [splits][rows_pad][kcap]  per-split hard-negative candidates (mining)
   int32_t* topk_i;
@@ -73,9 +76,13 @@ struct TcFwdArgs {
   int ct_base, ex_lo, ex_len, slot_base, slot_base_b;
   int n_total, n_pad, row_offset, n_rows, rows_pad, topk, mine, kcap;
   float inv_tau, c1, c0, ut2;
+  float m_limit;     // tau / 0.025: largest fixed maximum that cannot underflow a row's dominant terms
 };
 struct TcBwdPrepArgs {
-  const float* stats_all;
+  const float* stats;        // statistics of rows [stats_row0, ...): [..][STRIDE]
+  int stats_row0;
+  int j_lo, j_cnt;           // columns whose coefficients this launch computes
+  int use_label_counts;      // |A_f|, |A_m| from the label-derived global counts (own partials, before any exchange)
   const double* partials;
   const int32_t* labels;
   float *colA, *colAm, *colB, *colThr;
@@ -90,24 +97,30 @@ struct TcBwdArgs {
   const float *colA, *colB;
   const float *colAm, *colThr;   // mining
   const int32_t* colThrIdx;
-  const float* scalars;  // [0] = uniformity coefficient cu
-  float* dz_part;        // [splits][rows_pad][256]
+  const float* scalars;  // [0] = uniformity coefficient cu, [1] = exponent offset -M/tau log2(e)
+  float* dz_part;        // [slots][rows_pad][256]
   TcSched sched;
+  TcSched sched_b;       // reduce only: second pass of the two-phase backward (P == 0: none)
+  int ct_base, ex_lo, ex_len, slot_base, slot_base_b;
   int n_total, n_pad, row_offset, n_rows, rows_pad;
   float c1, c0, ut2;
 };
 TcPlan tc_plan(const supcon_problem_t* p);
 bool tc_supported(const supcon_problem_t* p);
 bool tc_two_phase(const supcon_problem_t* p);
+bool tc_bwd_two_phase(const supcon_problem_t* p);
 int tc_debug_plan(const supcon_problem_t* p, int32_t* out, int n_out);
 int tc_debug_sched(int T, int P, long long U, int cta, int row_block, long long* range_begin, long long* range_end,
                    int* first_cta, int* last_cta);
 int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, float* row_stats,
                double* partials, float* loss_out, void* workspace, cudaStream_t stream, const char** err,
                int phase = 0);
-int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, const float* stats_all,
-                const double* partials_global, const float* grad_out, void* dz_out, int dz_dtype, void* workspace,
-                cudaStream_t stream, const char** err);
+// phase: 0 = whole backward; 1 = only the columns this rank owns (`stats` = the rank's OWN statistics
+// [n_rows][STRIDE], `partials` = its own forward partials; partial dz records, nothing else is written);
+// 2 = all other columns (`stats` = everyone's, `partials` = the global sums) + reduce over both phases.
+int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, const float* stats,
+                const double* partials, const float* grad_out, void* dz_out, int dz_dtype, void* workspace,
+                cudaStream_t stream, const char** err, int phase = 0);
 
 // ---- single-launch small-batch path (supcon_small.cu) ----
 struct SmallArgs {

@@ -18,8 +18,14 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM
 // alloc), warps 2..9 = eight softmax/epilogue warps (two warpgroups).
-// Preconditions of this path (checked by the dispatcher): bf16 z, d == 256,
-// tau >= 0.025, rows L2-normalised (what the callers pass, stage1_utils.py:123).
+// Preconditions of this path (checked by the dispatcher): bf16 z, d == 256, tau >= 0.025 and, for cosine
+// similarity, the caller's promise SUPCON_FLAG_UNIT_ROWS (geodesic similarities lie in [-1, 1] whatever the
+// norms).  The exponentials use ONE fixed maximum M = max(1, max_j |z_j|^2) (every similarity is <= M by
+// Cauchy-Schwarz) found ON THE DEVICE by the prep kernel: M == 1 exactly for unit rows (max |z|^2 <= 1 + 2^-6
+// snaps to 1, bf16 rounding included).  A fixed maximum is only safe while no row's dominant terms can
+// underflow, i.e. while 2 M / tau <= 80; rows that break the promise beyond that (M > tau / 0.025) POISON the
+// result: every exponential becomes NaN and so do the loss and dz -- loud, never silently wrong.  Without the
+// promise such inputs take the exact path (online maximum), which handles any norms.
 #include <stdlib.h>
 
 #include "supcon_common.cuh"
@@ -96,22 +102,57 @@ __device__ __forceinline__ int label_table_count(const unsigned long long* keys,
   }
 }
 
-__global__ void tc_prep_fwd_kernel(const __nv_bfloat16* __restrict__ z, const int32_t* __restrict__ labels, int n,
-                                   int n_pad, int d, int32_t* __restrict__ lab_pad, float* __restrict__ nrm_pad,
-                                   int want_norms, int j_lo = 0, int ex_lo = 0x7fffffff, int ex_len = 0) {
-  // one warp per column j of [j_lo, n_pad), skipping the window [ex_lo, ex_lo + ex_len)
-  int warp = j_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (warp >= ex_lo) warp += ex_len;
-  if (warp >= n_pad) return;
-  float s = 0.f;
-  if (warp < n && want_norms) {
-    const __nv_bfloat16* zr = z + (int64_t)warp * d;
-    for (int k = lane; k < d; k += 32) { float v = __bfloat162float(zr[k]); s = fmaf(v, v, s); }
-    s = warp_sum(s);
+// workspace header (first 256 bytes, zeroed by the forward's memset): word 0 = ticket of the merge kernel,
+// word 4 = bits of max_j |z_j|^2 over the columns swept so far (non-negative floats order like unsigned ints)
+constexpr int WS_NRM2_MAX_WORD = 4;
+__device__ __forceinline__ float fixmax_from_bits(unsigned bits, float m_limit) {
+  const float m2 = __uint_as_float(bits);
+  if (m2 <= 1.015625f) return 1.0f;   // unit rows (bf16 rounding included): M == 1 exactly
+  return m2 <= m_limit ? m2 : __int_as_float(0x7fc00000);   // beyond tau / 0.025: poison (NaN), see the header
+}
+
+// padded labels + squared norms of `count` columns of [j_lo, n_pad) minus the window [ex_lo, ex_lo + ex_len),
+// and their running maximum (one atomic per block).  One warp per column, grid-stride.
+__global__ void __launch_bounds__(256) tc_prep_fwd_kernel(const __nv_bfloat16* __restrict__ z,
+                                                          const int32_t* __restrict__ labels, int n, int n_pad, int d,
+                                                          int32_t* __restrict__ lab_pad, float* __restrict__ nrm_pad,
+                                                          unsigned* __restrict__ nrm2_max, int count, int j_lo = 0,
+                                                          int ex_lo = 0x7fffffff, int ex_len = 0,
+                                                          int track_max = 1) {
+  __shared__ float wmax[8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float mx = 0.f;
+  for (int w = blockIdx.x * 8 + wib; w < count; w += gridDim.x * 8) {
+    int j = j_lo + w;
+    if (j >= ex_lo) j += ex_len;
+    if (j >= n_pad) break;
+    float s = 0.f;
+    if (j < n) {
+      const __nv_bfloat16* zr = z + (int64_t)j * d;
+      for (int k = 8 * lane; k < d; k += 256) {   // d % 8 == 0 on this path (d == 256): 16-byte loads
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(zr + k));
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[q]));
+          s = fmaf(f.x, f.x, s); s = fmaf(f.y, f.y, s);
+        }
+      }
+      s = warp_sum(s);
+    }
+    if (lane == 0) {
+      lab_pad[j] = j < n ? labels[j] : 0;
+      nrm_pad[j] = s;
+    }
+    mx = fmaxf(mx, s);
   }
-  if (lane == 0) {
-    lab_pad[warp] = warp < n ? labels[warp] : 0;
-    if (want_norms) nrm_pad[warp] = warp < n ? s : 0.f;
+  if (lane == 0) wmax[wib] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = wmax[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, wmax[i]);
+    if (track_max && m > 0.f) atomicMax(nrm2_max, __float_as_uint(m));   // geodesic: s in [-1, 1], M stays 1
   }
 }
 
@@ -141,25 +182,29 @@ __global__ void tc_label_table_kernel(const int32_t* __restrict__ labels, int n,
 //   e0_ij = exp((s_ij - 1)/tau);  H_ij = e0 (A_i + A_j) [+ mined terms] - pos_ij (B_i + B_j)
 //   A = a_f exp(1/tau - lse),  Am = a_m exp(1/tau - lse_m),  B = (a_f + a_m)/|pos|
 __global__ void tc_prep_bwd_kernel(TcBwdPrepArgs a) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.n_pad) return;
+  int j = a.j_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.j_lo + a.j_cnt) return;
   float A = 0.f, Am = 0.f, B = 0.f, thr = INFINITY;
   int ti = -1, lab = 0;
+  // fixed maximum the forward used (tensor-path statistics carry it; statistics of another path: M = 1)
+  const float Mp = (float)a.partials[SUPCON_P_FIXMAX];   // NaN = the forward poisoned the result: stays NaN
+  const float M = (Mp >= 1.0f || Mp != Mp) ? Mp : 1.0f;
   if (j < a.n_total) {
-    const GlobalCoef g = global_coef(a.partials, a.n_total, a.tau, a.alpha, a.lambda_uni, a.uni_t);
-    const float* s = a.stats_all + (int64_t)j * SUPCON_STATS_STRIDE;
+    const GlobalCoef g = global_coef(a.partials, a.n_total, a.tau, a.alpha, a.lambda_uni, a.uni_t,
+                                     a.use_label_counts != 0);
+    const float* s = a.stats + (int64_t)(j - a.stats_row0) * SUPCON_STATS_STRIDE;
     const int* si = reinterpret_cast<const int*>(s);
     int npos = si[SUPCON_ST_NPOS], nneg = si[SUPCON_ST_NNEG];
     bool in_f = npos > 0, in_m = in_f && nneg > 0 && a.topk >= 1;
     float af = in_f ? g.a_full : 0.f, am = in_m ? g.a_mined : 0.f;
-    float inv_tau = 1.0f / a.tau;
-    A = af * expf(inv_tau - s[SUPCON_ST_LSE]);
-    Am = (am != 0.f) ? am * expf(inv_tau - s[SUPCON_ST_LSE_M]) : 0.f;
+    float m_tau = M / a.tau;
+    A = af * expf(m_tau - s[SUPCON_ST_LSE]);
+    Am = (am != 0.f) ? am * expf(m_tau - s[SUPCON_ST_LSE_M]) : 0.f;
     B = in_f ? (af + am) / (float)npos : 0.f;
     thr = s[SUPCON_ST_THR_VAL];
     ti = si[SUPCON_ST_THR_IDX];
     lab = a.labels[j];
-    if (j == 0) a.scalars[0] = g.cu;
+    if (j == a.j_lo) { a.scalars[0] = g.cu; a.scalars[1] = -(LOG2E / a.tau) * M; }
   }
   a.colA[j] = A; a.colAm[j] = Am; a.colB[j] = B; a.colThr[j] = thr; a.colThrIdx[j] = ti; a.lab_pad[j] = lab;
 }
@@ -427,6 +472,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
     int* wl_i = reinterpret_cast<int*>(sZJ + STAGES * TILE_BYTES + 256 * LIST_STRIDE * 4) + (warp - 2) * 32 * LIST_STRIDE;
     const int K = a.kcap;
     const uint32_t taddr = tmem + lane_addr + TM_S + wg * BN;
+    // exponent offset of this launch: -M/tau * log2(e) with the fixed maximum as of this phase's prep kernel
+    const float c0 = -a.c1 * fixmax_from_bits(*a.nrm2_max, a.m_limit);
     int g = 0;
     for (long long u = u_begin; u < u_end;) {
       const int rb = (int)(u / sc.T), ct0 = (int)(u % sc.T);
@@ -464,15 +511,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
         const int32_t* lab_s = lab_ring[slot];
         const float* nrm_s = nrm_ring[UNI ? slot : 0];
         if (masked) {
-          fwd_chunk<SIM, UNI, MINE, true>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
-          fwd_chunk<SIM, UNI, MINE, true>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
-          fwd_chunk<SIM, UNI, MINE, true>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
-          fwd_chunk<SIM, UNI, MINE, true>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+          fwd_chunk<SIM, UNI, MINE, true>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
+          fwd_chunk<SIM, UNI, MINE, true>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
+          fwd_chunk<SIM, UNI, MINE, true>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
+          fwd_chunk<SIM, UNI, MINE, true>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
         } else {
-          fwd_chunk<SIM, UNI, MINE, false>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
-          fwd_chunk<SIM, UNI, MINE, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
-          fwd_chunk<SIM, UNI, MINE, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
-          fwd_chunk<SIM, UNI, MINE, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, a.c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+          fwd_chunk<SIM, UNI, MINE, false>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
+          fwd_chunk<SIM, UNI, MINE, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
+          fwd_chunk<SIM, UNI, MINE, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
+          fwd_chunk<SIM, UNI, MINE, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
         }
         if (MINE) {   // candidates re-read S from tensor memory: release the buffer only now
           ptx::tc_fence_before_sync();
@@ -483,7 +530,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
         const int slot_out = a.slot_base + (int)blockIdx.x - sched_cta_of(sc, (long long)rb * sc.T);
         const int64_t rec = (int64_t)slot_out * a.rows_pad + (gi - a.row_offset);
         float* out = a.part + rec * 8;
-        *reinterpret_cast<float4*>(out) = make_float4(st.sum_all, st.sum_pos_s, st.wsum, 0.f);
+        *reinterpret_cast<float4*>(out) = make_float4(st.sum_all, st.sum_pos_s, st.wsum, c0);   // [3]: offset used
         *reinterpret_cast<float4*>(out + 4) = make_float4(st.sum_pos_e, __int_as_float(ms.cnt), 0.f, 0.f);
         if (MINE) {
           for (int e = 0; e < ms.cnt; ++e) {
@@ -502,11 +549,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
 
 // merge the column splits into row statistics + loss partial sums
 __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishArgs f, float* __restrict__ row_stats) {
-  __shared__ double red[5 * 128];
+  __shared__ double red[7 * 128];
   __shared__ float mrg_v[TC_KCAP * 128];   // per-thread merge lists, entry-major (conflict-free)
   __shared__ int mrg_i[TC_KCAP * 128];
   const int lr = blockIdx.x * 128 + threadIdx.x;
   double l_full = 0.0, c_full = 0.0, l_mined = 0.0, c_mined = 0.0, w = 0.0;
+  // final fixed maximum (all columns seen): records of an earlier phase may carry a smaller one and are rescaled
+  const float M = fixmax_from_bits(*a.nrm2_max, a.m_limit);
+  const float c0 = -a.c1 * M, m_tau = M * a.inv_tau;
   if (lr < a.n_rows) {
     float sum_all = 0.f, sum_pos_s = 0.f, wsum = 0.f, sum_pos_e = 0.f;
     const int npos = label_table_count(a.hkeys, a.hcounts, a.hmask, a.lab_pad[a.row_offset + lr]) - 1;
@@ -526,11 +576,12 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
       for (int s = slot_lo[ps]; s < slot_lo[ps] + slot_n[ps]; ++s) {
         const float* rec = a.part + ((int64_t)s * a.rows_pad + lr) * 8;
         const float4 v = *reinterpret_cast<const float4*>(rec);
-        sum_all += v.x; sum_pos_s += v.y; wsum += v.z;
-        sum_pos_e += rec[4];
+        const float scale = (v.w == c0) ? 1.0f : ex2f(c0 - v.w);   // exp((M_rec - M)/tau) <= 1
+        sum_all = fmaf(v.x, scale, sum_all); sum_pos_s += v.y; wsum += v.z;
+        sum_pos_e = fmaf(rec[4], scale, sum_pos_e);
       }
     const int nneg = a.n_total - 1 - npos;
-    const float lse = logf(sum_all) + a.inv_tau;   // fixed maximum 1/tau folded back in
+    const float lse = logf(sum_all) + m_tau;   // fixed maximum M/tau folded back in
     const float pos_mean = npos > 0 ? (sum_pos_s * a.inv_tau) / (float)npos : 0.f;
     float lse_m = lse;
     float thr_val = a.topk >= 1 ? -INFINITY : INFINITY;
@@ -560,8 +611,8 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
           }
         }
       float sum_top = 0.f;
-      for (int e = 0; e < K; ++e) sum_top += ex2f(fmaf(mv[e * 128], a.c1, a.c0));
-      lse_m = logf(sum_pos_e + sum_top) + a.inv_tau;
+      for (int e = 0; e < K; ++e) sum_top += ex2f(fmaf(mv[e * 128], a.c1, c0));
+      lse_m = logf(sum_pos_e + sum_top) + m_tau;
       thr_val = mv[(K - 1) * 128];
       thr_idx = mi[(K - 1) * 128];
     }
@@ -580,10 +631,28 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
     }
     w = (double)wsum;
   }
+  // |A_f|, |A_m| of the GLOBAL batch from the class-size table (it holds every column by now): a class of
+  // size c contributes its c rows to A_f when c >= 2 and to A_m when also c < N (some negative exists).
+  // Every rank derives the same two integers, so the backward's coefficients need no exchange.
+  double g_full = 0.0, g_mined = 0.0;
+  {
+    const uint32_t hsize = a.hmask + 1u;
+    const uint32_t per = (hsize + gridDim.x - 1) / gridDim.x;
+    const uint32_t h_end = min(hsize, (blockIdx.x + 1u) * per);
+    for (uint32_t h = blockIdx.x * per + threadIdx.x; h < h_end; h += 128) {
+      if (a.hkeys[h] == 0ull) continue;
+      const int c = a.hcounts[h];
+      if (c >= 2) {
+        g_full += (double)c;
+        if (c < a.n_total && a.topk >= 1) g_mined += (double)c;
+      }
+    }
+  }
   red[0 * 128 + threadIdx.x] = l_full; red[1 * 128 + threadIdx.x] = c_full; red[2 * 128 + threadIdx.x] = l_mined;
   red[3 * 128 + threadIdx.x] = c_mined; red[4 * 128 + threadIdx.x] = w;
+  red[5 * 128 + threadIdx.x] = g_full; red[6 * 128 + threadIdx.x] = g_mined;
   __syncthreads();
-  block_partials_and_finish(f, red, 128);
+  block_partials_and_finish<7>(f, red, 128, (double)M);
 }
 
 // ---------------------------------------------------------------------------
@@ -602,7 +671,7 @@ struct RowMine {  // the same for this thread's row
 
 template <int SIM, bool UNI, bool MINE, bool MASKED>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw)[16], int gj0, int gi, int lab_r,
-                                          float A_r, float B_r, float nrm_r, float cu, const ColVecs& cv,
+                                          float A_r, float B_r, float nrm_r, float cu, float c0, const ColVecs& cv,
                                           const RowMine& rm, const TcBwdArgs& a) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -630,7 +699,7 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw
     for (int e = 0; e < 4; ++e) {
       const float c = __uint_as_float(r[4 * q + e]);
       const float s = (SIM == SUPCON_GEODESIC) ? geodesic_sim_fast(c) : c;
-      const float e0 = ex2f(fmaf(s, a.c1, a.c0));
+      const float e0 = ex2f(fmaf(s, a.c1, c0));
       float v = e0 * (A_r + As[e]);
       if (MINE) {
         // j in pos_i U top_i  /  i in pos_j U top_j, re-derived from the stored thresholds
@@ -653,11 +722,21 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw
   }
 }
 
+// logical column tile of this launch -> physical 64-column tile (same window scheme as the forward: the
+// two-phase multi-GPU backward first sweeps the rank's own columns, whose statistics it already has, while
+// the other ranks' statistics are still in flight, then everything else)
+__device__ __forceinline__ int bwd_col_tile(const TcBwdArgs& a, int ct) {
+  return a.ct_base + ct + (ct >= a.ex_lo ? a.ex_len : 0);
+}
+
 // Backward: a persistent CTA walks a contiguous range of the flattened (128-row block, 64-column
-// tile) work list.  Per segment Z_I lives in tensor memory (A operand of the S MMAs); the two
-// warpgroups take alternate tiles: pull S(t) into registers, form H(t) and write it back as packed
-// bf16 over the first 32 columns of the same S buffer, from where it is the A operand of
-// dZ += H Z_J (no shared-memory round trip).  Tensor-pipe order within a segment:
+// tile) work list.  Per segment Z_I lives in tensor memory (A operand of the S MMAs).  BOTH
+// warpgroups work on EVERY tile, warpgroup w on its 32-column half: pull that half of S(t) into
+// registers, form H(t) and write it back as packed bf16 over the first 16 columns of its own half of
+// the S buffer, from where it is the A operand of dZ += H Z_J (no shared-memory round trip).
+// Halving the columns per warpgroup halves the latency between "S(t) complete" and "H(t) ready" --
+// with alternating whole tiles that latency exceeded the S(t+1) + dZ(t-1) window the tensor pipe
+// can cover and the pipe idled ~28 % of the time (ncu r01).  Tensor-pipe order within a segment:
 // S(0) S(1) dZ(0) S(2) dZ(1) ...; tcgen05.mma executes in issue order, so S(t+2) cannot overwrite
 // the buffer dZ(t) is still reading.  Barriers are indexed by a running tile counter.
 template <int SIM, bool UNI, bool MINE>
@@ -689,7 +768,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
     ptx::mbar_init(&bar_done, 1);
     ptx::mbar_init(&bar_dzfree, 256);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_hfull[b], 128); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_hfull[b], 256); }
     for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
     ptx::fence_mbar_init();
     ptx::tma_prefetch_desc(&tmapJ);
@@ -708,7 +787,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
       for (int t = 0; t < nt; ++t, ++g) {
         const int st = g % STAGES, use = g / STAGES, slot = g % RING;
-        const int col0 = (ct0 + t) * BN;
+        const int col0 = bwd_col_tile(a, ct0 + t) * BN;
         // stage/slot st was last used by tile g-4; its release (dZ(g-4) complete) implies H(g-4) was formed
         ptx::mbar_wait(&bar_empty[st], (use & 1) ^ 1);
         if (ptx::elect_one()) {
@@ -780,7 +859,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
             const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
 #pragma unroll
             for (int kk = 0; kk < BN / 16; ++kk) {
-              ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + 8 * kk,
+              // H(t) columns 16 kk .. 16 kk + 15 as packed bf16: warpgroup (kk >> 1) left them at the start
+              // of its own 32-column half of the S buffer
+              ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + 32 * (kk >> 1) + 8 * (kk & 1),
                           ptx::smem_desc_sw128(b0 + kk * 16 * 128, BOXJ_BYTES, 1024), idesc_dz, (t > 1 || kk > 0));
             }
             ptx::mma_commit(&bar_empty[st]);
@@ -792,12 +873,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       }
     }
   } else {
-    // ===== H warpgroups: warpgroup w takes the tiles with (running index & 1) == w (S/H buffer w) =====
+    // ===== H warpgroups: both take every tile, warpgroup w its columns 32 w .. 32 w + 31 =====
     const int wg = (warp - 2) >> 2;
     const int lrow = 32 * (warp & 3) + lane;
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     const float cu = UNI ? a.scalars[0] : 0.f;
-    const uint32_t sbuf = tmem + lane_addr + TM_S + wg * BN;
+    const float c0 = a.scalars[1];   // -M/tau * log2(e), M = the forward's fixed maximum
     int g0 = 0, seg = 0;
     for (long long u = u_begin; u < u_end; ++seg) {
       const int rb = (int)(u / sc.T), ct0 = (int)(u % sc.T);
@@ -816,43 +897,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       const float nrm_r = UNI ? a.nrm_pad[gic] : 0.f;
       RowMine rm;
       rm.Am = MINE ? a.colAm[gic] : 0.f; rm.thr = MINE ? a.colThr[gic] : 0.f; rm.thr_idx = MINE ? a.colThrIdx[gic] : 0;
-      for (int t = ((g0 & 1) == wg ? 0 : 1); t < nt; t += 2) {
+      for (int t = 0; t < nt; ++t) {
         const int g = g0 + t;
-        const int buse = g >> 1, slot = g % RING;
-        const int col0 = (ct0 + t) * BN;
+        const int buf = g & 1, buse = g >> 1, slot = g % RING;
+        const int col0 = bwd_col_tile(a, ct0 + t) * BN;
+        const uint32_t sbuf = tmem + lane_addr + TM_S + buf * BN + 32 * wg;
         ptx::mbar_wait(&bar_col[slot], (g / RING) & 1);
-        ptx::mbar_wait(&bar_sfull[wg], buse & 1);
+        ptx::mbar_wait(&bar_sfull[buf], buse & 1);
         ptx::tc_fence_after_sync();
-        uint32_t r0[32], r1[32];
+        uint32_t r0[32];
         ptx::tmem_ld32(sbuf, r0);
-        ptx::tmem_ld32(sbuf + 32, r1);
         ptx::tmem_ld_wait();
-        uint32_t hw[32];
-        uint32_t (&h0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[0]);
-        uint32_t (&h1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[16]);
-        ColVecs cv0, cv1;
-        cv0.lab = lab_ring[slot]; cv0.A = colA_ring[slot]; cv0.B = colB_ring[slot]; cv0.nrm = nrm_ring[UNI ? slot : 0];
-        cv0.Am = colAm_ring[MINE ? slot : 0]; cv0.thr = thr_ring[MINE ? slot : 0]; cv0.thr_idx = thridx_ring[MINE ? slot : 0];
-        cv1.lab = cv0.lab + 32; cv1.A = cv0.A + 32; cv1.B = cv0.B + 32; cv1.nrm = cv0.nrm + 32;
-        cv1.Am = cv0.Am + 32; cv1.thr = cv0.thr + 32; cv1.thr_idx = cv0.thr_idx + 32;
+        uint32_t hw[16];
+        ColVecs cv;
+        cv.lab = lab_ring[slot] + 32 * wg; cv.A = colA_ring[slot] + 32 * wg; cv.B = colB_ring[slot] + 32 * wg;
+        cv.nrm = nrm_ring[UNI ? slot : 0] + 32 * wg;
+        cv.Am = colAm_ring[MINE ? slot : 0] + 32 * wg; cv.thr = thr_ring[MINE ? slot : 0] + 32 * wg;
+        cv.thr_idx = thridx_ring[MINE ? slot : 0] + 32 * wg;
         const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
-        if (masked) {
-          bwd_chunk<SIM, UNI, MINE, true>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, rm, a);
-          bwd_chunk<SIM, UNI, MINE, true>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, rm, a);
-        } else {
-          bwd_chunk<SIM, UNI, MINE, false>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, cv0, rm, a);
-          bwd_chunk<SIM, UNI, MINE, false>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, cv1, rm, a);
-        }
-        ptx::tmem_st32(sbuf, hw);            // H(t): 64 bf16 = 32 packed columns over S(t)
+        if (masked) bwd_chunk<SIM, UNI, MINE, true>(r0, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv, rm, a);
+        else bwd_chunk<SIM, UNI, MINE, false>(r0, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv, rm, a);
+        ptx::tmem_st16(sbuf, hw);            // this half of H(t): 32 bf16 = 16 packed columns over S(t)
         ptx::tmem_st_wait();
         ptx::tc_fence_before_sync();
-        ptx::mbar_arrive(&bar_hfull[wg]);
+        ptx::mbar_arrive(&bar_hfull[buf]);
       }
       // ---- segment epilogue: dZ rows out of TMEM; warpgroup w writes columns 128w..128w+127 ----
       ptx::mbar_wait(&bar_done, seg & 1);
       ptx::tc_fence_after_sync();
       const bool row_ok = gi < a.row_offset + a.n_rows;
-      const int slot_out = (int)blockIdx.x - sched_cta_of(sc, (long long)rb * sc.T);
+      const int slot_out = a.slot_base + (int)blockIdx.x - sched_cta_of(sc, (long long)rb * sc.T);
       float* outp = a.dz_part + ((int64_t)slot_out * a.rows_pad + (gi - a.row_offset)) * TD + 128 * wg;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -889,12 +963,20 @@ __global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const _
   if (lr >= a.n_rows) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int rb = lr / TBM;
-  const int nslots = sched_cta_of(a.sched, (long long)rb * a.sched.T + a.sched.T - 1) -
-                     sched_cta_of(a.sched, (long long)rb * a.sched.T) + 1;
-  for (int s = 0; s < nslots; ++s) {
-    const float4 v = *reinterpret_cast<const float4*>(a.dz_part + ((int64_t)s * a.rows_pad + lr) * TD + 4 * c4);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-  }
+  // pass A (a.sched, slots from a.slot_base) and, after a two-phase backward, pass B
+  int slot_lo[2], slot_n[2];
+  slot_lo[0] = a.slot_base;
+  slot_n[0] = sched_cta_of(a.sched, (long long)rb * a.sched.T + a.sched.T - 1) -
+              sched_cta_of(a.sched, (long long)rb * a.sched.T) + 1;
+  slot_lo[1] = a.slot_base_b;
+  slot_n[1] = a.sched_b.P > 0 ? sched_cta_of(a.sched_b, (long long)rb * a.sched_b.T + a.sched_b.T - 1) -
+                                    sched_cta_of(a.sched_b, (long long)rb * a.sched_b.T) + 1
+                              : 0;
+  for (int ps = 0; ps < 2; ++ps)
+    for (int s = slot_lo[ps]; s < slot_lo[ps] + slot_n[ps]; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(a.dz_part + ((int64_t)s * a.rows_pad + lr) * TD + 4 * c4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   const int gi = a.row_offset + lr;
   const float cu = a.scalars[0];
   if (cu != 0.f) {
@@ -915,18 +997,29 @@ __global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const _
   }
 }
 
+// Tuning knobs: read from the environment ONCE, when the library is first used (never on the launch path),
+// so that a plan is a pure function of the problem afterwards.  0 / unset = the built-in choice.
+struct TcKnobs {
+  int fwd_ctas, bwd_ctas, local_ctas, local_free_sms, bwd_local_free_sms;
+};
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
+const TcKnobs& knobs() {
+  static const TcKnobs k = {env_int("SUPCON_TC_FWD_CTAS", 0), env_int("SUPCON_TC_BWD_CTAS", 0),
+                            env_int("SUPCON_TC_LOCAL_CTAS", 0), env_int("SUPCON_TC_LOCAL_FREE_SMS", 32),
+                            env_int("SUPCON_TC_BWD_LOCAL_FREE_SMS", 16)};
+  return k;
+}
 
-TcSched make_sched(int row_blocks, int col_tiles, int num_sms, const char* env_ctas, int leave_free = 0) {
+TcSched make_sched(int row_blocks, int col_tiles, int num_sms, int forced_ctas, int leave_free = 0) {
   TcSched sc;
   sc.T = col_tiles;
   sc.U = (long long)row_blocks * col_tiles;
   // two CTAs' worth of work per SM: the hardware scheduler evens out SM-to-SM speed differences
   // (measured: rank share of N/8 rows 0.714 -> 0.694 ms), as long as a CTA still gets >= 32 tiles
-  long long p = env_int(env_ctas, 0);
+  long long p = forced_ctas;
   if (p <= 0 && leave_free > 0) p = num_sms > leave_free ? num_sms - leave_free : 1;   // one CTA per used SM
   if (p <= 0) p = (sc.U / (2LL * num_sms) >= 32) ? 2LL * num_sms : num_sms;
   if (p > sc.U) p = sc.U;
@@ -943,15 +1036,25 @@ int sched_max_slots(const TcSched& sc, int row_blocks) {
   return m;
 }
 
-int g_num_sms = 0;
+// SM count of the CURRENT device (a process may drive several devices: cached per device ordinal)
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  constexpr int MAX_DEV = 64;
+  static int cache[MAX_DEV] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();   // no device / no driver (CPU-side plan introspection): the B200 count
+    return 148;
   }
-  return g_num_sms;
+  if (dev < 0 || dev >= MAX_DEV) dev = 0;
+  int n = cache[dev];
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = 148;
+    }
+    cache[dev] = n;
+  }
+  return n;
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -961,30 +1064,41 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ---- workspace layout shared by forward and backward ----
 TcPlan tc_plan(const supcon_problem_t* p) {
   TcPlan pl;
+  const TcKnobs& kn = knobs();
+  const int sms = num_sms();
   pl.n_pad = (int)align_up((size_t)p->n_total, 128);
   pl.rows_pad = (int)align_up((size_t)p->n_rows, 128);
   pl.row_blocks = pl.rows_pad / 128;
   pl.fwd_row_blocks = (pl.row_blocks + 1) / 2;   // forward CTAs own two 128-row blocks
   pl.fwd_col_tiles = pl.n_pad / 128;
   pl.bwd_col_tiles = (p->n_total + 63) / 64;
-  pl.fwd_sched = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles, num_sms(), "SUPCON_TC_FWD_CTAS");
-  pl.bwd_sched = make_sched(pl.row_blocks, pl.bwd_col_tiles, num_sms(), "SUPCON_TC_BWD_CTAS");
+  pl.fwd_sched = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles, sms, kn.fwd_ctas);
+  pl.bwd_sched = make_sched(pl.row_blocks, pl.bwd_col_tiles, sms, kn.bwd_ctas);
   pl.fwd_slots = sched_max_slots(pl.fwd_sched, pl.fwd_row_blocks);
   pl.bwd_slots = sched_max_slots(pl.bwd_sched, pl.row_blocks);
-  // two-phase forward (multi-GPU overlap): phase 1 sweeps the rank's own columns, phase 2 the others
+  // two-phase sweeps (multi-GPU overlap): phase 1 covers the rank's own columns, phase 2 the others
   pl.two_phase = (p->n_rows < p->n_total) && (p->row_offset % 128 == 0) && (p->n_rows % 128 == 0);
   pl.local_ct0 = p->row_offset / 128;
   pl.local_cts = p->n_rows / 128;
+  pl.bwd_local_ct0 = p->row_offset / 64;
+  pl.bwd_local_cts = p->n_rows / 64;
+  pl.slots_local = pl.bwd_slots_local = 0;
   if (pl.two_phase) {
-    // the own-column phase runs beside the NCCL all-gather kernel: leave SMs free for its channels (a CTA of
-    // this kernel fills an SM, so the collective could not co-reside and the two would serialise)
+    // an own-column phase runs beside an NCCL all-gather kernel: leave SMs free for its channels (a CTA of
+    // these kernels fills an SM, so the collective could not co-reside and the two would serialise)
     // (only when that phase is short, i.e. the rank owns at most a quarter of the columns)
-    const int free_sms = (4 * pl.local_cts <= pl.fwd_col_tiles) ? env_int("SUPCON_TC_LOCAL_FREE_SMS", 32) : 0;
-    pl.fwd_sched_local = make_sched(pl.fwd_row_blocks, pl.local_cts, num_sms(), "SUPCON_TC_LOCAL_CTAS", free_sms);
-    pl.fwd_sched_remote = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles - pl.local_cts, num_sms(), "SUPCON_TC_FWD_CTAS");
+    const bool small_share = 4 * pl.local_cts <= pl.fwd_col_tiles;
+    pl.fwd_sched_local = make_sched(pl.fwd_row_blocks, pl.local_cts, sms, kn.local_ctas,
+                                    small_share ? kn.local_free_sms : 0);
+    pl.fwd_sched_remote = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles - pl.local_cts, sms, kn.fwd_ctas);
     pl.slots_local = sched_max_slots(pl.fwd_sched_local, pl.fwd_row_blocks);
     int both = pl.slots_local + sched_max_slots(pl.fwd_sched_remote, pl.fwd_row_blocks);
     if (both > pl.fwd_slots) pl.fwd_slots = both;
+    pl.bwd_sched_local = make_sched(pl.row_blocks, pl.bwd_local_cts, sms, 0, small_share ? kn.bwd_local_free_sms : 0);
+    pl.bwd_sched_remote = make_sched(pl.row_blocks, pl.bwd_col_tiles - pl.bwd_local_cts, sms, kn.bwd_ctas);
+    pl.bwd_slots_local = sched_max_slots(pl.bwd_sched_local, pl.row_blocks);
+    both = pl.bwd_slots_local + sched_max_slots(pl.bwd_sched_remote, pl.row_blocks);
+    if (both > pl.bwd_slots) pl.bwd_slots = both;
   }
   pl.merge_blocks = pl.rows_pad / 128;
   size_t off = 256;
@@ -1017,11 +1131,13 @@ TcPlan tc_plan(const supcon_problem_t* p) {
 // host-side introspection for the CPU tests of the work distribution (no device work)
 int tc_debug_plan(const supcon_problem_t* p, int32_t* out, int n_out) {
   const TcPlan pl = tc_plan(p);
-  const int32_t v[12] = {pl.fwd_sched.P, pl.fwd_sched.T, pl.fwd_slots, pl.bwd_sched.P, pl.bwd_sched.T, pl.bwd_slots,
+  const int32_t v[16] = {pl.fwd_sched.P, pl.fwd_sched.T, pl.fwd_slots, pl.bwd_sched.P, pl.bwd_sched.T, pl.bwd_slots,
                          pl.two_phase ? 1 : 0, pl.two_phase ? pl.fwd_sched_local.P : 0,
                          pl.two_phase ? pl.fwd_sched_remote.P : 0, pl.two_phase ? pl.slots_local : 0,
-                         pl.fwd_row_blocks, pl.row_blocks};
-  for (int i = 0; i < n_out && i < 12; ++i) out[i] = v[i];
+                         pl.fwd_row_blocks, pl.row_blocks,
+                         pl.two_phase ? pl.bwd_sched_local.P : 0, pl.two_phase ? pl.bwd_sched_remote.P : 0,
+                         pl.two_phase ? pl.bwd_slots_local : 0, pl.two_phase ? pl.bwd_sched_local.T : 0};
+  for (int i = 0; i < n_out && i < 16; ++i) out[i] = v[i];
   return 0;
 }
 int tc_debug_sched(int T, int P, long long U, int cta, int row_block, long long* range_begin, long long* range_end,
@@ -1038,6 +1154,9 @@ int tc_debug_sched(int T, int P, long long U, int cta, int row_block, long long*
 bool tc_supported(const supcon_problem_t* p) {
   if (p->z_dtype != SUPCON_BF16 || p->d != TD) return false;
   if (!(p->tau >= 0.025f)) return false;
+  // cosine similarities are bounded by the row norms: the fixed-maximum evaluation needs the caller's promise
+  // that rows are (near) unit norm; forcing the tensor path asserts it too.  Verified on the device (NaN if broken).
+  if (p->similarity == SUPCON_COSINE && !(p->flags & (SUPCON_FLAG_UNIT_ROWS | SUPCON_FLAG_FORCE_TENSOR))) return false;
   if (p->alpha != 0.f && p->topk > TC_KCAP) return false;   // in-sweep top-K lists hold at most 32 entries
   if (p->n_total < 256) return false;
   return true;
@@ -1059,6 +1178,9 @@ static cudaError_t launch_fwd_m(bool mine, const CUtensorMap& tm, const __nv_bfl
 }
 
 bool tc_two_phase(const supcon_problem_t* p) { return tc_supported(p) && tc_plan(p).two_phase; }
+// the own-column backward needs every global coefficient before the exchange: |A_f|, |A_m| come from the
+// gathered labels, but the uniformity coefficient needs the global sum of W
+bool tc_bwd_two_phase(const supcon_problem_t* p) { return tc_two_phase(p) && !(p->lambda_uni > 0.f); }
 
 // phase: 0 = whole forward; 1 = only the columns this rank owns (partial records, needs nothing from other
 // ranks); 2 = all other columns + merge.  Phases 1 and 2 must use the same workspace.
@@ -1078,19 +1200,23 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
   }
   const bool uni = p->lambda_uni > 0.f;
+  unsigned* nrm2_max = reinterpret_cast<unsigned*>(ws) + WS_NRM2_MAX_WORD;
   {
-    // padded labels / squared norms of the columns this phase sweeps
+    // padded labels / squared norms (+ their maximum: the fixed maximum of the exponentials) of the columns
+    // this phase sweeps
     int j_lo = 0, ex_lo = 0x7fffffff, ex_len = 0, count = pl.n_pad;
-    if (phase == 1) { j_lo = pl.local_ct0 * 128; count = pl.local_cts * 128; ex_lo = j_lo + count; ex_len = pl.n_pad; }
+    if (phase == 1) { j_lo = pl.local_ct0 * 128; count = pl.local_cts * 128; }
     if (phase == 2) { ex_lo = pl.local_ct0 * 128; ex_len = pl.local_cts * 128; count = pl.n_pad - ex_len; }
-    int threads = 256, warps_per_block = threads / 32;
-    int blocks = (count + warps_per_block - 1) / warps_per_block;
-    if (blocks > 0)
-      tc_prep_fwd_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all,
-                                                         p->n_total, pl.n_pad, p->d,
-                                                         reinterpret_cast<int32_t*>(ws + pl.off_lab),
-                                                         reinterpret_cast<float*>(ws + pl.off_nrm), uni ? 1 : 0, j_lo,
-                                                         ex_lo, ex_len);
+    if (count > 0) {
+      int blocks = (count + 7) / 8;
+      const int cap = 8 * num_sms();   // grid-stride: one atomic per block
+      if (blocks > cap) blocks = cap;
+      tc_prep_fwd_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all,
+                                                     p->n_total, pl.n_pad, p->d,
+                                                     reinterpret_cast<int32_t*>(ws + pl.off_lab),
+                                                     reinterpret_cast<float*>(ws + pl.off_nrm), nrm2_max, count, j_lo,
+                                                     ex_lo, ex_len, p->similarity == SUPCON_COSINE ? 1 : 0);
+    }
     // class-size table over the (real) columns of this phase
     int jn_lo = j_lo, jn_ex_lo = ex_lo, jn_ex_len = ex_len, jn_count = p->n_total;
     if (phase == 1) { jn_count = p->n_rows; jn_ex_lo = jn_lo + jn_count; jn_ex_len = p->n_total; }
@@ -1100,10 +1226,12 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
           labels_all, p->n_total, reinterpret_cast<unsigned long long*>(ws + pl.off_hkeys),
           reinterpret_cast<int*>(ws + pl.off_hcounts), pl.hash_size - 1, jn_lo, jn_ex_lo, jn_ex_len);
   }
+  (void)uni;
   TcFwdArgs a;
   a.hkeys = reinterpret_cast<const unsigned long long*>(ws + pl.off_hkeys);
   a.hcounts = reinterpret_cast<const int*>(ws + pl.off_hcounts);
   a.hmask = pl.hash_size - 1;
+  a.nrm2_max = nrm2_max;
   a.ct_base = 0; a.ex_lo = 0x7fffffff; a.ex_len = 0; a.slot_base = 0;
   a.sched_b.P = 0; a.sched_b.T = 1; a.sched_b.U = 1; a.slot_base_b = 0;
   a.lab_pad = reinterpret_cast<const int32_t*>(ws + pl.off_lab);
@@ -1114,7 +1242,8 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
   if (phase == 1) { a.sched = pl.fwd_sched_local; a.ct_base = pl.local_ct0; }
   if (phase == 2) { a.sched = pl.fwd_sched_remote; a.ex_lo = pl.local_ct0; a.ex_len = pl.local_cts; a.slot_base = pl.slots_local; }
   a.inv_tau = 1.0f / p->tau;
-  a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
+  a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;   // c0: unit-row value; kernels derive theirs
+  a.m_limit = p->tau / 0.025f;
   const bool mine = p->alpha != 0.f && p->topk >= 1;
   a.mine = mine ? 1 : 0;
   a.kcap = mine ? (p->topk < TC_KCAP ? p->topk : TC_KCAP) : 0;
@@ -1157,9 +1286,9 @@ static cudaError_t launch_bwd_m(bool mine, const CUtensorMap& tmJ, const __nv_bf
   return mine ? launch_bwd<SIM, UNI, true>(tmJ, z, a, ctas, smem, st) : launch_bwd<SIM, UNI, false>(tmJ, z, a, ctas, smem, st);
 }
 
-int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, const float* stats_all,
-                const double* partials_global, const float* grad_out, void* dz_out, int dz_dtype, void* workspace,
-                cudaStream_t stream, const char** err) {
+int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, const float* stats,
+                const double* partials, const float* grad_out, void* dz_out, int dz_dtype, void* workspace,
+                cudaStream_t stream, const char** err, int phase) {
   const TcPlan pl = tc_plan(p);
   char* ws = reinterpret_cast<char*>(workspace);
   CUtensorMap tmJ;
@@ -1169,15 +1298,21 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   }
   const bool uni = p->lambda_uni > 0.f;
   cudaError_t e;
-  if (uni) {  // squared norms (labels are re-copied by the bwd prep below)
-    int threads = 256, blocks = (pl.n_pad + 7) / 8;
-    tc_prep_fwd_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all,
-                                                       p->n_total, pl.n_pad, p->d,
-                                                       reinterpret_cast<int32_t*>(ws + pl.off_lab),
-                                                       reinterpret_cast<float*>(ws + pl.off_nrm), 1);
+  if (uni) {  // squared norms (labels are re-copied by the bwd prep below); never in a two-phase backward
+    int blocks = (pl.n_pad + 7) / 8;
+    const int cap = 8 * num_sms();
+    if (blocks > cap) blocks = cap;
+    // the maximum goes to a scratch word of the scalars block: the backward takes M from the partials
+    tc_prep_fwd_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all,
+                                                   p->n_total, pl.n_pad, p->d,
+                                                   reinterpret_cast<int32_t*>(ws + pl.off_lab),
+                                                   reinterpret_cast<float*>(ws + pl.off_nrm),
+                                                   reinterpret_cast<unsigned*>(ws + pl.off_scalars) + 8, pl.n_pad);
   }
   TcBwdPrepArgs pa;
-  pa.stats_all = stats_all; pa.partials = partials_global; pa.labels = labels_all;
+  pa.stats = stats; pa.partials = partials; pa.labels = labels_all;
+  pa.stats_row0 = 0; pa.j_lo = 0; pa.j_cnt = pl.n_pad; pa.use_label_counts = 0;
+  if (phase == 1) { pa.stats_row0 = p->row_offset; pa.j_lo = p->row_offset; pa.j_cnt = p->n_rows; pa.use_label_counts = 1; }
   pa.colA = reinterpret_cast<float*>(ws + pl.off_colA); pa.colAm = reinterpret_cast<float*>(ws + pl.off_colAm);
   pa.colB = reinterpret_cast<float*>(ws + pl.off_colB); pa.colThr = reinterpret_cast<float*>(ws + pl.off_colThr);
   pa.colThrIdx = reinterpret_cast<int32_t*>(ws + pl.off_colThrIdx);
@@ -1185,7 +1320,7 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   pa.scalars = reinterpret_cast<float*>(ws + pl.off_scalars);
   pa.n_total = p->n_total; pa.n_pad = pl.n_pad; pa.topk = p->topk;
   pa.tau = p->tau; pa.alpha = p->alpha; pa.lambda_uni = p->lambda_uni; pa.uni_t = p->uni_t;
-  tc_prep_bwd_kernel<<<(pl.n_pad + 255) / 256, 256, 0, stream>>>(pa);
+  tc_prep_bwd_kernel<<<(pa.j_cnt + 255) / 256, 256, 0, stream>>>(pa);
   e = cudaGetLastError();
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
 
@@ -1196,10 +1331,17 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   a.dz_part = reinterpret_cast<float*>(ws + pl.off_part);
   a.n_total = p->n_total; a.n_pad = pl.n_pad; a.row_offset = p->row_offset; a.n_rows = p->n_rows;
   a.rows_pad = pl.rows_pad; a.sched = pl.bwd_sched;
+  a.sched_b.P = 0; a.sched_b.T = 1; a.sched_b.U = 1; a.slot_base_b = 0;
+  a.ct_base = 0; a.ex_lo = 0x7fffffff; a.ex_len = 0; a.slot_base = 0;
+  if (phase == 1) { a.sched = pl.bwd_sched_local; a.ct_base = pl.bwd_local_ct0; }
+  if (phase == 2) {
+    a.sched = pl.bwd_sched_remote; a.ex_lo = pl.bwd_local_ct0; a.ex_len = pl.bwd_local_cts;
+    a.slot_base = pl.bwd_slots_local;
+  }
   a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
   a.scalars = pa.scalars;
   const size_t smem = 6 * (size_t)NBOX * 64 * 128 + 1024;   // 6 x 32 KB Z_J stages
-  const int ctas = pl.bwd_sched.P;
+  const int ctas = a.sched.P;
   const bool geo = p->similarity == SUPCON_GEODESIC;
   const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
   const bool mine = p->alpha != 0.f && p->topk >= 1;
@@ -1208,14 +1350,19 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   else if (uni) e = launch_bwd_m<SUPCON_COSINE, true>(mine, tmJ, zb, a, ctas, smem, stream);
   else e = launch_bwd_m<SUPCON_COSINE, false>(mine, tmJ, zb, a, ctas, smem, stream);
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  if (phase == 1) return 0;   // partial dz records only; phase 2 reduces both
+  if (phase == 2) {           // the reduce sums the own-column records (pass A) and the others (pass B)
+    a.sched_b = a.sched; a.slot_base_b = a.slot_base;
+    a.sched = pl.bwd_sched_local; a.slot_base = 0;
+  }
   const int64_t n4 = (int64_t)p->n_rows * (TD / 4);
   const int blocks = (int)((n4 + 255) / 256);
   if (dz_dtype == SUPCON_BF16)
     tc_bwd_reduce_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<const __nv_bfloat16*>(z_all),
-                                                                    stats_all, grad_out,
+                                                                    stats, grad_out,
                                                                     reinterpret_cast<__nv_bfloat16*>(dz_out));
   else
-    tc_bwd_reduce_kernel<float><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<const __nv_bfloat16*>(z_all), stats_all,
+    tc_bwd_reduce_kernel<float><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<const __nv_bfloat16*>(z_all), stats,
                                                             grad_out, reinterpret_cast<float*>(dz_out));
   e = cudaGetLastError();
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }

@@ -3,17 +3,23 @@
 Rank r holds the embeddings/labels of its local batch = rows
 [r*n_local, (r+1)*n_local) of the global N x N similarity matrix:
 
-  forward   all_gather(z) + all_gather(labels)          (one coalesced NCCL launch over NVLink)
-            row-block forward kernel  -> row stats + 8 partial sums
-            all_gather(partial sums) + all_gather(row stats, N x 32 B)   (one coalesced launch;
-            the partials are summed in rank order on every rank: deterministic)
-            -> scalar loss (identical on every rank)
-  backward  row-block backward kernel: dz_i = sum_j (G_ij + G_ji) z_j for the
-            owned rows, recomputing the tiles.  Because the similarity matrix
-            is symmetric the column-side term G_ji only needs the *statistics*
+  forward   all_gather(z) + all_gather(labels)          (one coalesced NCCL launch over NVLink, on a side
+            stream) WHILE the forward kernel sweeps the rank's own columns; then the other columns
+            -> row stats + 8 partial sums
+            all_gather(partial sums) + all_gather(row stats, N x 32 B)   (one coalesced launch on the side
+            stream; one kernel sums the partials in rank order on every rank -- deterministic -- and writes
+            the scalar loss, identical on every rank) WHILE the backward kernel already sweeps the rank's own
+            columns, which need only its own statistics (the global anchor counts come from the gathered
+            labels).  This speculative part of the backward is issued from forward() when z needs a gradient.
+  backward  the other columns of the row-block backward: dz_i = sum_j (G_ij + G_ji) z_j for the
+            owned rows, recomputing the tiles, + the sum of both phases scaled by grad_out.  Because the
+            similarity matrix is symmetric the column-side term G_ji only needs the *statistics*
             of row j, so no N x d reduce-scatter of column partials is needed
             (deviation from the north_star plan, SURVEY H4/H6: the exchange is
             N x 32 B of statistics instead of N x d x 4 B of gradients).
+
+Every rank must hold the SAME number of local rows (checked once per distinct local size with an all-reduce of
+min/max; ragged shards raise instead of hanging NCCL).
 
 The result equals the single-GPU loss on the concatenated batch (what the
 reference's nn.DataParallel computes, train_stage1.py:82-84).  The returned
@@ -49,6 +55,10 @@ class _CudaKernels:
     # two-phase forward: own columns while the all-gather is in flight, then the rest
     forward_rows_local = staticmethod(Fn.forward_rows_local)
     forward_rows_remote = staticmethod(Fn.forward_rows_remote)
+    # two-phase backward: own columns while the statistics are exchanged, then the rest
+    backward_rows_local = staticmethod(Fn.backward_rows_local)
+    backward_rows_remote = staticmethod(Fn.backward_rows_remote)
+    finalize_sets = staticmethod(Fn.finalize_sets)
 
 
 _COMM_STREAMS = {}
@@ -136,11 +146,62 @@ def exchange_stats(partials: torch.Tensor, stats: torch.Tensor, group=None):
         with _coalesced(group, stats.device):
             dist.all_gather_into_tensor(p_all, p32, group=group)
             dist.all_gather_into_tensor(stats_all, stats.contiguous(), group=group)
-        partials.copy_(p_all.view(torch.float64).view(world, -1).sum(dim=0))
+        sets = p_all.view(torch.float64).view(world, -1)
+        summed = sets.sum(dim=0)
+        summed[5:] = sets[0, 5:]        # global label-derived counts / fixed maximum: identical on every rank
+        partials.copy_(summed)
     else:   # generic fallback (CPU stand-in kernels in the gloo tests)
+        keep = partials[5:].clone()
         dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+        partials[5:] = keep
         dist.all_gather_into_tensor(stats_all, stats.contiguous(), group=group)
     return stats_all
+
+
+def exchange_and_local_backward(z_all, labels_all, prob, stats, partials, group, kernels, want_grad=True):
+    """The exchange after the forward, overlapped with the part of the backward that does not need it.
+
+    Side stream: ONE coalesced NCCL launch {all-gather partial sums, all-gather row statistics}, then one kernel
+    that sums the partials in rank order and writes the scalar loss.  Current stream, meanwhile (only when a
+    gradient is wanted): the backward over the rank's OWN columns.  Returns (stats_all, partials_global, loss,
+    workspace of the started backward or None)."""
+    world = dist.get_world_size(group)
+    dev = stats.device
+    cur, comm = torch.cuda.current_stream(dev), _comm_stream(dev)
+    stats_all = torch.empty((world * stats.size(0), stats.size(1)), dtype=stats.dtype, device=dev)
+    p32 = partials.view(torch.float32)
+    p_all = torch.empty(world * p32.numel(), dtype=torch.float32, device=dev)
+    comm.wait_stream(cur)
+    with torch.cuda.stream(comm):
+        with _coalesced(group, dev):
+            dist.all_gather_into_tensor(p_all, p32, group=group)
+            if want_grad:
+                dist.all_gather_into_tensor(stats_all, stats, group=group)
+        partials_global, loss = kernels.finalize_sets(prob, p_all.view(torch.float64))
+    for t in (stats_all, p_all, partials_global, loss, stats, partials):
+        t.record_stream(comm)
+    ws = kernels.backward_rows_local(z_all, labels_all, stats, partials, prob) if want_grad else None
+    cur.wait_stream(comm)
+    return stats_all, partials_global, loss, ws
+
+
+_CHECKED_SHARDS = set()
+
+
+def check_equal_shards(n_local: int, device, group=None):
+    """Every rank must contribute the same number of rows (row_offset = rank * n_local; all_gather_into_tensor
+    needs equal shards).  Verified once per distinct local size: a ragged last batch raises here instead of
+    hanging or corrupting the collective."""
+    key = (id(group), n_local)
+    if key in _CHECKED_SHARDS:
+        return
+    t = torch.tensor([n_local, -n_local], device=device, dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    lo, hi = -int(t[1]), int(t[0])
+    if lo != hi:
+        raise ValueError(f"ShardedSupConLoss needs the same local batch size on every rank (got between {lo} and {hi} "
+                         f"rows): use drop_last / the equal-step BalancedBatchSampler")
+    _CHECKED_SHARDS.add(key)
 
 
 class _ShardedSupCon(torch.autograd.Function):
@@ -148,31 +209,52 @@ class _ShardedSupCon(torch.autograd.Function):
     def forward(ctx, z_local, labels_local, cfg, group, kernels):
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         zc = Fn.canonical_z(z_local.detach())
+        check_equal_shards(zc.size(0), zc.device, group)
 
         def make_prob(n_total, d, row_offset, n_rows):
             return Fn.make_problem(n_total, d, Fn._dtype_id(zc), row_offset=row_offset, n_rows=n_rows, **cfg)
 
         z_all, labels_all, prob, stats, partials = gather_and_forward(zc, labels_local, make_prob, group, kernels)
-        if ctx.needs_input_grad[0]:
-            stats_all = exchange_stats(partials, stats, group)
+        want_grad = ctx.needs_input_grad[0]
+        overlap = zc.device.type == "cuda" and hasattr(kernels, "backward_rows_local")
+        ws = None
+        if overlap:
+            stats_all, partials, loss, ws = exchange_and_local_backward(z_all, labels_all, prob, stats, partials,
+                                                                        group, kernels, want_grad)
         else:
-            dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
-        loss = kernels.finalize(prob, partials)
-        if ctx.needs_input_grad[0]:
+            if want_grad:
+                stats_all = exchange_stats(partials, stats, group)
+            else:
+                keep = partials[5:].clone()
+                dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+                partials[5:] = keep
+            loss = kernels.finalize(prob, partials)
+        if want_grad:
             ctx.save_for_backward(z_all, labels_all, stats_all, partials)
             ctx.prob, ctx.kernels, ctx.in_dtype, ctx.work_dtype = prob, kernels, z_local.dtype, zc.dtype
+            ctx.ws = ws
         return Fn._loss_dtype(loss, z_local.dtype)
 
     @staticmethod
     def backward(ctx, grad_out):
         z_all, labels_all, stats_all, partials = ctx.saved_tensors
-        dz = ctx.kernels.backward_rows(z_all, labels_all, stats_all, partials, grad_out, ctx.prob, ctx.work_dtype)
+        if ctx.ws is not None:
+            dz = ctx.kernels.backward_rows_remote(z_all, labels_all, stats_all, partials, grad_out, ctx.prob, ctx.ws,
+                                                  out_dtype=ctx.work_dtype)
+            ctx.ws = None
+        else:
+            dz = ctx.kernels.backward_rows(z_all, labels_all, stats_all, partials, grad_out, ctx.prob, ctx.work_dtype)
         return dz.to(ctx.in_dtype), None, None, None, None
 
 
 class ShardedSupConLoss(torch.nn.Module):
     """SupConBinaryLoss over the global batch of all ranks (same constructor and
-    call signature as reference loss.py:19-25,110-114, plus ``group``)."""
+    call signature as reference loss.py:19-25,110-114, plus ``group``).
+
+    Every rank must pass the same number of rows per call (equal shards; checked, a mismatch raises).
+    When ``z`` requires a gradient, forward() already launches the part of the backward that needs no
+    exchange (the rank's own columns) so that it overlaps the all-gather of the row statistics; a second
+    backward() through the same graph (retain_graph) recomputes the whole backward."""
 
     def __init__(self, temperature: float = 0.2, similarity: str = "geodesic", uniformity_weight: float = 0.0,
                  uniformity_t: float = 2.0, group: Optional[dist.ProcessGroup] = None, kernels=None):
@@ -185,13 +267,16 @@ class ShardedSupConLoss(torch.nn.Module):
         self.group = group
         self.kernels = kernels if kernels is not None else _CudaKernels
         self.kernel_flags = 0
+        self.assume_unit_rows = None   # see SupConBinaryLoss.assume_unit_rows
 
     def forward(self, z: torch.Tensor, labels: torch.Tensor, topk_neg: int = 32, alpha: float = 0.0):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("ShardedSupConLoss needs an initialised torch.distributed process group")
         if self.kernels is _CudaKernels:
             Fn._require_cuda(z, "z")
-        cfg = dict(tau=self.tau, similarity=Fn.similarity_id(self.similarity), lambda_uni=self.lambda_uni,
-                   uni_t=self.uni_t, topk=topk_neg, alpha=alpha, flags=self.kernel_flags)
+        sim = Fn.similarity_id(self.similarity)
+        cfg = dict(tau=self.tau, similarity=sim, lambda_uni=self.lambda_uni,
+                   uni_t=self.uni_t, topk=topk_neg, alpha=alpha,
+                   flags=self.kernel_flags | Fn.unit_rows_flag(z, sim, self.assume_unit_rows))
         lab = Fn.canonical_labels(labels, z.size(0))
         return _ShardedSupCon.apply(z, lab, cfg, self.group, self.kernels)

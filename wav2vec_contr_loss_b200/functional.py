@@ -67,21 +67,63 @@ def canonical_labels(labels: torch.Tensor, n: int) -> torch.Tensor:
     return lab.contiguous()
 
 
+_PROBLEMS = {}          # argument tuple -> Problem (host structs are immutable once built: safe to share)
+_WORKSPACE_BYTES = {}   # (problem fields, device index) -> bytes: the size is asked of the library once per shape
+
+
 def make_problem(n_total, d, z_dtype_id, *, tau, similarity, lambda_uni=0.0, uni_t=2.0, topk=32,
                  alpha=0.0, row_offset=0, n_rows=None, flags=0) -> _cabi.Problem:
-    topk = max(0, min(int(topk), 2**31 - 1))
-    return _cabi.Problem(
-        n_total=int(n_total), row_offset=int(row_offset),
-        n_rows=int(n_total if n_rows is None else n_rows), d=int(d), z_dtype=int(z_dtype_id),
-        similarity=int(similarity), topk=topk, flags=int(flags), tau=float(tau), alpha=float(alpha),
-        lambda_uni=float(lambda_uni), uni_t=float(uni_t))
+    key = (n_total, d, z_dtype_id, tau, similarity, lambda_uni, uni_t, topk, alpha, row_offset, n_rows, flags)
+    prob = _PROBLEMS.get(key)
+    if prob is None:
+        k = max(0, min(int(topk), 2**31 - 1))
+        prob = _cabi.Problem(
+            n_total=int(n_total), row_offset=int(row_offset),
+            n_rows=int(n_total if n_rows is None else n_rows), d=int(d), z_dtype=int(z_dtype_id),
+            similarity=int(similarity), topk=k, flags=int(flags), tau=float(tau), alpha=float(alpha),
+            lambda_uni=float(lambda_uni), uni_t=float(uni_t))
+        if len(_PROBLEMS) > 4096:   # alpha changes every epoch: bound the cache
+            _PROBLEMS.clear()
+        _PROBLEMS[key] = prob
+    return prob
+
+
+def _problem_key(prob: _cabi.Problem):
+    return (prob.n_total, prob.row_offset, prob.n_rows, prob.d, prob.z_dtype, prob.similarity, prob.topk, prob.flags,
+            prob.tau, prob.alpha, prob.lambda_uni, prob.uni_t)
+
+
+def workspace_bytes(prob: _cabi.Problem, device) -> int:
+    """Scratch bytes the library wants for this problem on this device (asked once per shape and cached: the
+    plan depends on the device's SM count)."""
+    key = (_problem_key(prob), getattr(device, "index", None))
+    n = _WORKSPACE_BYTES.get(key)
+    if n is None:
+        lib = _cabi.load()
+        nbytes = ctypes.c_size_t(0)
+        import contextlib
+        on_gpu = getattr(device, "type", None) == "cuda"
+        with (torch.cuda.device(device) if on_gpu else contextlib.nullcontext()):   # the plan uses this device's SMs
+            _cabi.check(lib.supcon_workspace_bytes(ctypes.byref(prob), ctypes.byref(nbytes)), "supcon_workspace_bytes")
+        n = max(int(nbytes.value), 256)
+        if len(_WORKSPACE_BYTES) > 4096:
+            _WORKSPACE_BYTES.clear()
+        _WORKSPACE_BYTES[key] = n
+    return n
 
 
 def workspace_for(prob: _cabi.Problem, device) -> torch.Tensor:
-    lib = _cabi.load()
-    nbytes = ctypes.c_size_t(0)
-    _cabi.check(lib.supcon_workspace_bytes(ctypes.byref(prob), ctypes.byref(nbytes)), "supcon_workspace_bytes")
-    return torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=device)
+    return torch.empty(workspace_bytes(prob, device), dtype=torch.uint8, device=device)
+
+
+def _stats_buffers(n_rows: int, dev, want_loss: bool = True):
+    """row statistics [n_rows, 8] f32 + partial sums [8] f64 + the scalar loss in ONE allocation."""
+    words = n_rows * _cabi.STATS_STRIDE
+    buf = torch.empty(words + 2 * _cabi.N_PARTIALS + 2, dtype=torch.float32, device=dev)
+    stats = buf[:words].view(n_rows, _cabi.STATS_STRIDE)
+    partials = buf[words:words + 2 * _cabi.N_PARTIALS].view(torch.float64)   # byte offset 32 n_rows: 8-aligned
+    loss = buf[words + 2 * _cabi.N_PARTIALS] if want_loss else None
+    return stats, partials, loss
 
 
 def forward_rows(z_all: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Problem, want_loss: bool):
@@ -90,9 +132,7 @@ def forward_rows(z_all: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Prob
     lib = _cabi.load()
     dev = z_all.device
     with torch.cuda.device(dev):
-        stats = torch.empty((prob.n_rows, _cabi.STATS_STRIDE), dtype=torch.float32, device=dev)
-        partials = torch.empty(_cabi.N_PARTIALS, dtype=torch.float64, device=dev)
-        loss = torch.empty((), dtype=torch.float32, device=dev) if want_loss else None
+        stats, partials, loss = _stats_buffers(prob.n_rows, dev, want_loss)
         ws = workspace_for(prob, dev)
         _cabi.check(lib.supcon_forward_rows(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(stats),
                                             _p(partials), _p(loss), _p(ws), ws.numel(), _stream(dev)),
@@ -108,9 +148,7 @@ def loss_and_grad(z: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Problem
     lib = _cabi.load()
     dev = z.device
     with torch.cuda.device(dev):
-        stats = torch.empty((prob.n_rows, _cabi.STATS_STRIDE), dtype=torch.float32, device=dev)
-        partials = torch.empty(_cabi.N_PARTIALS, dtype=torch.float64, device=dev)
-        loss = torch.empty((), dtype=torch.float32, device=dev)
+        stats, partials, loss = _stats_buffers(prob.n_rows, dev, True)
         dz = torch.empty((prob.n_rows, prob.d), dtype=out_dtype, device=dev) if want_grad else None
         ws = workspace_for(prob, dev)
         _cabi.check(lib.supcon_loss_and_grad(ctypes.byref(prob), _p(z), _p(labels_i32), _p(loss), _p(dz),
@@ -142,8 +180,7 @@ def forward_rows_remote(z_all, labels_i32, prob: _cabi.Problem, ws: torch.Tensor
     lib = _cabi.load()
     dev = z_all.device
     with torch.cuda.device(dev):
-        stats = torch.empty((prob.n_rows, _cabi.STATS_STRIDE), dtype=torch.float32, device=dev)
-        partials = torch.empty(_cabi.N_PARTIALS, dtype=torch.float64, device=dev)
+        stats, partials, _ = _stats_buffers(prob.n_rows, dev, False)
         _cabi.check(lib.supcon_forward_rows_remote(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(stats),
                                                    _p(partials), _p(ws), ws.numel(), _stream(dev)),
                     "supcon_forward_rows_remote")
@@ -158,6 +195,49 @@ def finalize(prob: _cabi.Problem, partials_global: torch.Tensor) -> torch.Tensor
         _cabi.check(lib.supcon_finalize(ctypes.byref(prob), _p(partials_global), _p(loss), _stream(dev)),
                     "supcon_finalize")
     return loss
+
+
+def finalize_sets(prob: _cabi.Problem, partial_sets: torch.Tensor):
+    """Rank-ordered sum of every rank's partial sums [R, 8] f64 + the scalar loss, one launch.
+    Returns (partials_global [8] f64, loss)."""
+    lib = _cabi.load()
+    dev = partial_sets.device
+    with torch.cuda.device(dev):
+        out = torch.empty(_cabi.N_PARTIALS + 1, dtype=torch.float64, device=dev)
+        partials, loss = out[:_cabi.N_PARTIALS], out[_cabi.N_PARTIALS:].view(torch.float32)[0]
+        _cabi.check(lib.supcon_finalize_sets(ctypes.byref(prob), _p(partial_sets), partial_sets.numel() // _cabi.N_PARTIALS,
+                                             _p(partials), _p(loss), _stream(dev)), "supcon_finalize_sets")
+    return partials, loss
+
+
+def backward_rows_local(z_all, labels_i32, stats_local, partials_local, prob: _cabi.Problem) -> torch.Tensor:
+    """Phase 1 of the two-phase row-block backward: the rank's own columns, from its own statistics only
+    (no exchange needed yet, no grad_out needed yet).  Returns the workspace backward_rows_remote must be given."""
+    lib = _cabi.load()
+    dev = z_all.device
+    with torch.cuda.device(dev):
+        ws = workspace_for(prob, dev)
+        _cabi.check(lib.supcon_backward_rows_local(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(stats_local),
+                                                   _p(partials_local), _p(ws), ws.numel(), _stream(dev)),
+                    "supcon_backward_rows_local")
+    return ws
+
+
+def backward_rows_remote(z_all, labels_i32, stats_all, partials_global, grad_out, prob: _cabi.Problem, ws,
+                         out_dtype=torch.float32) -> torch.Tensor:
+    """Phase 2: all other columns + sum of both phases, scaled by grad_out."""
+    lib = _cabi.load()
+    dev = z_all.device
+    with torch.cuda.device(dev):
+        dz = torch.empty((prob.n_rows, prob.d), dtype=out_dtype, device=dev)
+        g = None
+        if grad_out is not None:
+            g = grad_out.detach().reshape(()).to(device=dev, dtype=torch.float32)
+        _cabi.check(lib.supcon_backward_rows_remote(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(stats_all),
+                                                    _p(partials_global), _p(g), _p(dz), _dtype_id(dz), _p(ws),
+                                                    ws.numel(), _stream(dev)),
+                    "supcon_backward_rows_remote")
+    return dz
 
 
 def backward_rows(z_all, labels_i32, stats_all, partials_global, grad_out, prob: _cabi.Problem,
@@ -232,15 +312,47 @@ class SupConFunction(torch.autograd.Function):
         return dz.to(ctx.in_dtype), None, None, None, None, None, None, None, None
 
 
+UNIT_ROWS_TAG = "_supcon_unit_rows"   # set on tensors produced by this library's row normalisation
+_warned_untagged = False
+
+
+def mark_unit_rows(z: torch.Tensor) -> torch.Tensor:
+    """Tag ``z`` as having L2-normalised rows (done by l2_normalize / FusedCompressionHead.embed).  The tag is a
+    plain attribute of this tensor object: views, casts and copies do not carry it."""
+    setattr(z, UNIT_ROWS_TAG, True)
+    return z
+
+
+def unit_rows_flag(z: torch.Tensor, similarity_id_: int, unit_rows) -> int:
+    """SUPCON_FLAG_UNIT_ROWS when the caller promises (unit_rows=True) or the tensor carries this library's tag
+    (unit_rows=None).  Only a bf16, d = 256, cosine problem is affected: it reaches the tensor-core path under
+    the promise and the exact path (z taken as given, any norms) without it."""
+    global _warned_untagged
+    if unit_rows is None:
+        unit_rows = bool(getattr(z, UNIT_ROWS_TAG, False))
+        if (not unit_rows and not _warned_untagged and z.dtype == torch.bfloat16 and z.dim() == 2
+                and z.size(1) == 256 and z.size(0) >= 256 and similarity_id_ == _cabi.COSINE):
+            _warned_untagged = True
+            import warnings
+            warnings.warn("SupCon: bf16 z of width 256 that was not produced by l2_normalize()/embed() is taken as "
+                          "given on the exact fp32 path (any row norms).  If its rows are L2-normalised, set "
+                          "loss.assume_unit_rows = True (or pass unit_rows=True) to use the tensor-core path.",
+                          stacklevel=3)
+    return _cabi.FLAG_UNIT_ROWS if unit_rows else 0
+
+
 def supcon_loss(z, labels, *, temperature, similarity="cosine", uniformity_weight=0.0, uniformity_t=2.0,
-                topk_neg=32, alpha=0.0, flags=0) -> torch.Tensor:
-    """Functional form of SupConBinaryLoss.forward (reference loss.py:110-153)."""
+                topk_neg=32, alpha=0.0, flags=0, unit_rows=None) -> torch.Tensor:
+    """Functional form of SupConBinaryLoss.forward (reference loss.py:110-153).  ``unit_rows``: None = rows are
+    known to be L2-normalised only if ``z`` came from this library's l2_normalize / embed; True = the caller
+    promises it (checked on the device: a broken promise gives NaN, never a silently wrong number)."""
     sim_id = similarity_id(similarity) if isinstance(similarity, str) else int(similarity)
     n = z.size(0)
     if n < 2:
         # reference loss.py:138-139,149: no anchor has a positive and the uniformity term needs B > 1
         return torch.tensor(0.0, device=z.device, requires_grad=True)
     lab = canonical_labels(labels, n)
+    flags = int(flags) | unit_rows_flag(z, sim_id, unit_rows)
     return SupConFunction.apply(z, lab, float(temperature), sim_id, float(uniformity_weight),
                                 float(uniformity_t), int(topk_neg), float(alpha), int(flags))
 
@@ -282,4 +394,4 @@ class _NormalizeFunction(torch.autograd.Function):
 
 
 def l2_normalize(x: torch.Tensor, out_dtype=torch.float32) -> torch.Tensor:
-    return _NormalizeFunction.apply(x, out_dtype)
+    return mark_unit_rows(_NormalizeFunction.apply(x, out_dtype))

@@ -29,12 +29,16 @@ class SupConBinaryLoss(nn.Module):
         if self.similarity not in ("cosine", "geodesic"):
             raise ValueError(f"Unknown similarity: {similarity}")
         self.kernel_flags = 0
+        # None: rows count as L2-normalised only when z came from this library's l2_normalize()/embed();
+        # True: the caller promises it (bf16 cosine inputs then take the tensor-core path; checked on the device)
+        self.assume_unit_rows = None
 
     def forward(self, z: torch.Tensor, labels: torch.Tensor, topk_neg: int = 32,
                 alpha: float = 0.0) -> torch.Tensor:
         return supcon_loss(z, labels, temperature=self.tau, similarity=self.similarity,
                            uniformity_weight=self.lambda_uni, uniformity_t=self.uni_t,
-                           topk_neg=topk_neg, alpha=alpha, flags=self.kernel_flags)
+                           topk_neg=topk_neg, alpha=alpha, flags=self.kernel_flags,
+                           unit_rows=self.assume_unit_rows)
 
 
 class SupConMultiClassLoss(nn.Module):
@@ -47,11 +51,12 @@ class SupConMultiClassLoss(nn.Module):
         super().__init__()
         self.tau = temperature
         self.kernel_flags = 0
+        self.assume_unit_rows = None
 
     def forward(self, z: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         assert labels.dim() == 1 and labels.size(0) == z.size(0), "labels must be shape (B,)"
         return supcon_loss(z, labels, temperature=self.tau, similarity="cosine", uniformity_weight=0.0,
-                           topk_neg=0, alpha=0.0, flags=self.kernel_flags)
+                           topk_neg=0, alpha=0.0, flags=self.kernel_flags, unit_rows=self.assume_unit_rows)
 
 
 class BCEBinaryLoss(nn.Module):
