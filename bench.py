@@ -262,108 +262,100 @@ def workload_config(args, extra=None):
 
 
 def run_stage1(args):
-    """BASELINE configs[4]: the caller's Stage-1 step (reference stage1_utils.py:110-132) around the loss, on a
-    random-init XLS-R-300M (no checkpoints offline) and synthetic 4 s / 16 kHz audio, batch 64 per GPU, frozen
-    encoder (CLI default finetune_encoder=0, stage1_config.py:30), compression head trained with AdamW.
-    Reports ms/step and the share of the step spent in the loss (forward + backward to z) for three losses:
-    this library, a vectorised torch restatement (cuBLAS + logsumexp: what a careful user would write), and the
-    per-anchor loop port of the reference's loss.py (the baseline leg: oracle/supcon_oracle.py)."""
+    """BASELINE configs[4] through the reference's UNCHANGED callers (oracle/_ref, staged verbatim by
+    oracle/build_ref.py): encoder.Wav2Vec2Encoder (encoder.py:11-70) on a random-init XLS-R-300M saved locally
+    (no checkpoints offline), compression_module.CompressionModule(1024, 256, 0.1) and
+    stage1_utils.train_one_epoch (stage1_utils.py:102-134) over synthetic 4 s / 16 kHz audio, batch 64 per GPU,
+    frozen encoder (CLI default finetune_encoder=0, stage1_config.py:30), AdamW on the head.  Several GPUs exactly as
+    train_stage1.py:82-84 does it: nn.DataParallel over encoder and head in ONE process, so the loss sees the
+    gathered batch (64 x n_gpus) on cuda:0.  The only thing that changes between the two timed runs is which
+    object is passed as loss_fn: the reference's loss.py class or this repo's drop-in.  Reports ms/step and the
+    loss's share of the step (loss fwd+bwd alone on the same embeddings, host-inclusive)."""
+    import tempfile
+    from types import SimpleNamespace
     import torch
-    import torch.nn as nn
-    import torch.nn.functional as F
     from transformers import Wav2Vec2Config, Wav2Vec2Model
     from wav2vec_contr_loss_b200 import build as _build
     _build.build()
     from wav2vec_contr_loss_b200 import SupConBinaryLoss
-    from oracle import supcon_oracle as O
+    from oracle import ref_loader as R
+    root = R.reference_root()
+    if root is None:
+        print(json.dumps({"workload": "stage1_step", "unavailable": "reference not staged (oracle/_ref missing)"}))
+        return
+    sys.path.insert(0, root)
+    import compression_module as ref_head      # noqa: E402  (the reference's own files, unedited)
+    import encoder as ref_encoder              # noqa: E402
+    import stage1_utils as ref_utils           # noqa: E402
+    ref_loss = R.load_reference_module("loss")
 
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(dev)
-    torch.manual_seed(1337)
-    cfg = Wav2Vec2Config(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
-                         feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True, conv_dim=(512,) * 7,
-                         conv_stride=(5, 2, 2, 2, 2, 2, 2), conv_kernel=(10, 3, 3, 3, 3, 2, 2),
-                         num_conv_pos_embeddings=128, num_conv_pos_embedding_groups=16, layerdrop=0.0)
-    encoder = Wav2Vec2Model(cfg).to(dev).eval()
-    for p_ in encoder.parameters():
-        p_.requires_grad = False
+    ngpu = max(1, min(args.gpus, torch.cuda.device_count()))
+    dev = torch.device("cuda")                  # as train_stage1.py:28
+    ref_utils.set_seed(1337)
+    cfg_m = Wav2Vec2Config(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
+                           feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True, conv_dim=(512,) * 7,
+                           conv_stride=(5, 2, 2, 2, 2, 2, 2), conv_kernel=(10, 3, 3, 3, 3, 2, 2),
+                           num_conv_pos_embeddings=128, num_conv_pos_embedding_groups=16, layerdrop=0.0)
+    tmp = tempfile.mkdtemp(prefix="xlsr300m_random_")
+    Wav2Vec2Model(cfg_m).save_pretrained(tmp)
+    enc = ref_encoder.Wav2Vec2Encoder(model_name=tmp, freeze_encoder=True).to(dev)
+    n_params = sum(p_.numel() for p_ in enc.parameters())
+    B = args.stage1_batch * ngpu
+    g = torch.Generator().manual_seed(1337)
+    steps = max(3, min(args.steps, 8))
+    batches = [(torch.randn(B, 64000, generator=g), (torch.arange(B) % 2).long()) for _ in range(steps)]
+    cfg = SimpleNamespace(finetune_encoder=False, use_rawboost=False, topk_neg=args.topk, warmup_epochs=0,
+                          alpha_ramp_epochs=1, alpha_end=args.alpha)      # epoch 1 -> alpha = alpha_end
 
-    class LayerMeanHead(nn.Module):   # shape/ops of the reference's compression head (compression_module.py:35-67)
-        def __init__(self):
-            super().__init__()
-            self.drop, self.act, self.proj = nn.Dropout(0.1), nn.LeakyReLU(), nn.Linear(1024, 256)
+    def make_loss(kind):
+        cls = ref_loss.SupConBinaryLoss if kind == "reference_loss_py" else SupConBinaryLoss
+        return cls(temperature=args.tau, similarity=args.similarity, uniformity_weight=args.lambda_uni,
+                   uniformity_t=2.0)
 
-        def forward(self, hs):        # (B, K, F, T) -> (B, 256, T)
-            x = self.act(self.drop(hs.mean(dim=1)))
-            return self.proj(x.transpose(1, 2)).transpose(1, 2)
-
-    head = LayerMeanHead().to(dev).train()
-    opt = torch.optim.AdamW(head.parameters(), lr=1e-4)
-    B = args.stage1_batch
-    wave = torch.randn(B, 64000, device=dev)
-    labels = (torch.arange(B, device=dev) % 2).long()
-    tau, topk, alpha = args.tau, args.topk, args.alpha
-
-    def vectorised_loss(z, y):        # plain torch restatement of the full SupCon term (cosine, alpha = 0)
-        n = z.size(0)
-        lg = (z @ z.t()) / tau
-        eye = torch.eye(n, dtype=torch.bool, device=z.device)
-        lg = lg.masked_fill(eye, float("-inf"))
-        pos = (y.view(-1, 1) == y.view(1, -1)) & ~eye
-        lse = torch.logsumexp(lg, dim=1)
-        npos = pos.sum(1)
-        per = lse - (lg.masked_fill(~pos, 0.0).sum(1) / npos.clamp_min(1))
-        return per[npos > 0].mean()
-
-    ours = SupConBinaryLoss(temperature=tau, similarity=args.similarity, uniformity_weight=args.lambda_uni)
-    losses = {
-        "b200_kernel": lambda z, y: ours(z, y, topk_neg=topk, alpha=alpha),
-        "torch_vectorised": vectorised_loss,
-        "reference_port": lambda z, y: O.anchor_loop_loss(z, y, temperature=tau, similarity=args.similarity,
-                                                          uniformity_weight=args.lambda_uni, topk_neg=topk, alpha=alpha),
-    }
-
-    def embed():
-        with torch.no_grad():
-            out = encoder(wave, attention_mask=torch.ones_like(wave, dtype=torch.long), output_hidden_states=True)
-            hs = torch.stack(out.hidden_states, dim=0).transpose(0, 1).permute(0, 1, 3, 2).contiguous()
-        return F.normalize(head(hs).mean(dim=-1), p=2, dim=1)
-
-    def full_step(loss_fn):
-        z = embed()
-        loss = loss_fn(z, labels)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(head.parameters(), 5.0)
-        opt.step()
-        return loss.item()
-
-    def timed(fn, reps):
+    result = {"workload": "stage1_step (BASELINE configs[4])", "n_gpus": ngpu, "batch_per_gpu": args.stage1_batch,
+              "global_batch": B, "encoder": f"random-init XLS-R-300M ({n_params / 1e6:.1f} M params), frozen",
+              "callers": "UNCHANGED reference files from oracle/_ref: encoder.Wav2Vec2Encoder, "
+                         "compression_module.CompressionModule, stage1_utils.train_one_epoch"
+                         + ("; nn.DataParallel over encoder and head as train_stage1.py:82-84" if ngpu > 1 else ""),
+              "audio": "synthetic 4 s @ 16 kHz", "similarity": args.similarity, "tau": args.tau, "topk": args.topk,
+              "alpha": cfg.alpha_end, "timed_steps": steps, "step_ms": {}, "loss_fwd_bwd_ms": {},
+              "loss_share_of_step": {}, "epoch_mean_loss": {}}
+    z_fixed = None
+    for kind in ("b200_dropin", "reference_loss_py"):
+        ref_utils.set_seed(1337)
+        head = ref_head.CompressionModule(1024, 256, 0.1).to(dev)
+        e_run, h_run = enc, head
+        if ngpu > 1:
+            e_run = torch.nn.DataParallel(enc, device_ids=list(range(ngpu)))
+            h_run = torch.nn.DataParallel(head, device_ids=list(range(ngpu)))
+        opt = torch.optim.AdamW([{"params": h_run.parameters(), "lr": 1e-4}], weight_decay=3e-3)
+        loss_fn = make_loss(kind)
+        ref_utils.train_one_epoch(e_run, h_run, loss_fn, batches[:2], opt, dev, 1, cfg)      # warm-up
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(reps):
-            fn()
+        avg, _ = ref_utils.train_one_epoch(e_run, h_run, loss_fn, batches, opt, dev, 1, cfg)
         torch.cuda.synchronize()
-        return 1e3 * (time.perf_counter() - t0) / reps
+        result["step_ms"][kind] = 1e3 * (time.perf_counter() - t0) / steps
+        result["epoch_mean_loss"][kind] = avg
+        if z_fixed is None:
+            with torch.no_grad():
+                w = batches[0][0].to(dev)
+                hs = e_run(w, attention_mask=(w != 0.0).long())
+                z_fixed = torch.nn.functional.normalize(h_run(hs).mean(dim=-1), p=2, dim=1).detach()
+        y = batches[0][1].to(dev)
 
-    z_fixed = embed().detach()
-
-    def loss_only(loss_fn):
-        z = z_fixed.clone().requires_grad_(True)
-        loss_fn(z, labels).backward()
-
-    result = {"workload": "stage1_step (BASELINE configs[4])", "batch": B, "encoder": "random-init XLS-R-300M, frozen",
-              "audio": "synthetic 4 s @ 16 kHz", "similarity": args.similarity, "tau": tau, "alpha": alpha,
-              "encoder_params_M": round(sum(p_.numel() for p_ in encoder.parameters()) / 1e6, 1),
-              "step_ms": {}, "loss_fwd_bwd_ms": {}, "loss_share_of_step": {}, "loss_value": {}}
-    for name, fn in losses.items():
-        for _ in range(max(2, args.warmup)):
-            full_step(fn)
-        result["loss_value"][name] = full_step(fn)
-        result["step_ms"][name] = timed(lambda: full_step(fn), max(3, min(args.steps, 10)))
-        loss_only(fn)
-        result["loss_fwd_bwd_ms"][name] = timed(lambda: loss_only(fn), 20)
-        result["loss_share_of_step"][name] = result["loss_fwd_bwd_ms"][name] / result["step_ms"][name]
+        def loss_only():
+            zz = z_fixed.clone().requires_grad_(True)
+            loss_fn(zz, y, topk_neg=cfg.topk_neg, alpha=cfg.alpha_end).backward()
+        loss_only()
+        torch.cuda.synchronize()
+        reps = 20 if kind == "b200_dropin" else 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            loss_only()
+        torch.cuda.synchronize()
+        result["loss_fwd_bwd_ms"][kind] = 1e3 * (time.perf_counter() - t0) / reps
+        result["loss_share_of_step"][kind] = result["loss_fwd_bwd_ms"][kind] / result["step_ms"][kind]
     print(json.dumps(result), flush=True)
 
 
