@@ -64,6 +64,9 @@ def parse():
                     help="loss: the SupCon hot path (default, BASELINE configs[3]); stage1: one Stage-1 training step "
                          "around it (BASELINE configs[4]) reporting the loss's share of the step")
     ap.add_argument("--stage1-batch", type=int, default=64)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="several ranks: how rows and row statistics travel -- peer = this library's kernels store "
+                         "into the peers' buffers over NVLink (symmetric memory), nccl = torch.distributed all-gathers")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the N = 64 / 1024 / mined side measurements (one GPU only)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
@@ -408,12 +411,15 @@ def main():
     # reference's -- loss = loss_fn(z, labels, topk_neg=..., alpha=...); loss.backward() -- on one GPU
     # SupConBinaryLoss, on several ShardedSupConLoss (same signature, rows of the global batch per rank).
     cls = ShardedSupConLoss if world > 1 else SupConBinaryLoss
-    loss_fn = cls(temperature=args.tau, similarity=args.similarity, uniformity_weight=args.lambda_uni, uniformity_t=2.0)
+    extra_kw = {"exchange": args.exchange} if world > 1 else {}
+    loss_fn = cls(temperature=args.tau, similarity=args.similarity, uniformity_weight=args.lambda_uni, uniformity_t=2.0,
+                  **extra_kw)
     loss_fn.kernel_flags = args.flags
     loss_fn.assume_unit_rows = True
     # kernels of libsupcon_b200.so per step on the tensor path.  One GPU: prep_fwd, label_table, tc_fwd, merge,
     # prep_bwd, tc_bwd, reduce.  Several ranks: forward in two phases (prep + label_table + tc_fwd twice, merge),
     # finalize_sets, backward in two phases (prep_bwd + tc_bwd twice), reduce.
+    # Peer exchange: push, forward in two phases (7), wait, push, wait, finalize_sets, backward (3), end_step = 16.
     launches_per_step = 7 if world == 1 else 14
     launches = {"count": 0}
 
@@ -461,6 +467,11 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step(z_local, y_local)
     barrier()
+    exchange_used = "none"
+    if world > 1:
+        exchange_used = "peer" if any(v is not None for v in loss_fn._peers.values()) else "nccl"
+        if exchange_used == "peer":
+            launches_per_step = 16
 
     # ---- host-inclusive time of the same call issued eagerly from Python (both figures) ----
     def eager_ms(fn, reps):
@@ -596,6 +607,10 @@ def main():
         fwd_tflops = pairs / world * flop_per_pair_fwd / (fwd_ms * 1e-3) / 1e12
         total_tflops = pairs * (flop_per_pair_bwd + flop_per_pair_fwd) / (ms_per_step * 1e-3) / 1e12
         cfg = workload_config(args)
+        cfg["exchange"] = {"none": "single GPU", "nccl": "NCCL all-gathers (torch.distributed) overlapped with the "
+                           "own-column phases of forward and backward",
+                           "peer": "peer-memory stores over NVLink by this library's kernels (symmetric memory), "
+                                   "rows pushed beside the own-column forward"}[exchange_used]
         cfg["api"] = (f"{cls.__name__}(temperature, similarity, ...)(z, labels, topk_neg, alpha) + autograd backward "
                       f"(the reference's call, stage1_utils.py:125-128); assume_unit_rows=True")
         line = {

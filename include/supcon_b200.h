@@ -52,6 +52,9 @@ extern "C" {
  * this promise (its exponentials use one fixed maximum); without it z is taken as given on the exact path.
  * The promise is CHECKED on the device: max_i |z_i|^2 > tau / 0.025 makes the loss and dz NaN. */
 #define SUPCON_FLAG_UNIT_ROWS 32u
+/* The two-phase calls run beside this library's own (small) peer-push kernel, not beside a collective
+ * library's kernel: their own-column phases use every SM instead of leaving some free for its channels. */
+#define SUPCON_FLAG_PEER_EXCHANGE 64u
 
 /* error codes */
 #define SUPCON_E_INVALID (-1)
@@ -170,6 +173,39 @@ int supcon_backward_rows_remote(const supcon_problem_t* p, const void* z_all, co
                                 const float* stats_all, const double* partials_global, const float* grad_out,
                                 void* dz_out, int32_t dz_dtype, void* workspace, size_t workspace_bytes,
                                 void* stream);
+
+/* ---- exchange between ranks through peer memory (NVLink / NVSwitch), see csrc/supcon_peer.cu -------------
+ * The host maps every rank's exchange buffer into every process (a symmetric allocation, e.g.
+ * torch.distributed._symmetric_memory) and describes it here.  All kernels are this library's own: plain
+ * stores to peer addresses + per-rank step flags; no collective library call inside a step, CUDA-graph
+ * capturable.  Replaces the all-gather of z / labels and of the row statistics (north_star's NCCL plan,
+ * SURVEY 8e) where peer access exists; the NCCL path of distributed.py remains the fallback. */
+#define SUPCON_PEER_MAX_WORLD 64
+#define SUPCON_PEER_FLAG_Z 0      /* rows of z + labels of step e have landed          */
+#define SUPCON_PEER_FLAG_STATS 1  /* row statistics + partial sums of step e have landed */
+#define SUPCON_PEER_FLAG_DONE 2   /* rank has finished step e (its buffers may be overwritten) */
+#define SUPCON_PEER_NFLAGS 3
+/* bytes every buffer reserves at off_flags, zeroed once at set-up: int32 flags[NFLAGS][world] + a ticket word */
+#define SUPCON_PEER_FLAG_BYTES(world) ((SUPCON_PEER_NFLAGS * (world) + 4) * 4)
+
+typedef struct supcon_peer {
+  int32_t rank, world;
+  const uint64_t* peer_bases; /* DEVICE array [world]: base address of every rank's buffer as mapped in THIS
+                                 process (peer_bases[rank] = the own buffer)                                 */
+  uint64_t off_flags;         /* byte offset of the flag block inside each buffer                           */
+  int32_t* epoch;             /* DEVICE int, rank-local: number of the current step, initialised to 1       */
+} supcon_peer_t;
+
+/* Copy up to two byte ranges (sizes multiples of 4; src1 may be NULL) to the same offsets of EVERY peer's buffer
+ * (and the own one if include_self), then set flag[flag_id][rank] = epoch in every buffer.
+ * wait_flag_id >= 0: first wait until flag[wait_flag_id][p] >= epoch - 1 for all p (buffer reuse guard). */
+int supcon_peer_push(const supcon_peer_t* pe, const void* src0, size_t bytes0, uint64_t dst_off0,
+                     const void* src1, size_t bytes1, uint64_t dst_off1, int32_t flag_id, int32_t wait_flag_id,
+                     int32_t include_self, void* stream);
+/* One-block kernel: returns (on the stream) when flag[flag_id][p] >= epoch for every rank p. */
+int supcon_peer_wait(const supcon_peer_t* pe, int32_t flag_id, void* stream);
+/* End of a step: flag[flag_id][rank] = epoch in every buffer, then epoch += 1. */
+int supcon_peer_end_step(const supcon_peer_t* pe, int32_t flag_id, void* stream);
 
 /* Whole batch on one GPU: loss and (if dz_out != NULL) d loss / d z in as few
  * launches as the shape allows (one for small batches).  row_stats/partials

@@ -52,14 +52,16 @@ def _rank_loss_and_grad(rank, world, port, out):
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
     try:
         res = {}
-        for (name, n, dt, sim, tau, lam, k, alpha, kind, classes) in CASES:
+        for (name, n, dt, sim, tau, lam, k, alpha, kind, classes), exchange in [(c, e) for e in ("nccl", "peer")
+                                                                              for c in CASES]:
+            name = f"{name}/{exchange}"
             dtype = torch.bfloat16 if dt == "bf16" else torch.float32
             x, y = O.make_inputs(n, 256, kind, classes=classes)
             z = F.normalize(x, dim=1).to(dtype)
             nl = n // world
             zl = z[rank * nl:(rank + 1) * nl].to(dev).requires_grad_(True)
             yl = y[rank * nl:(rank + 1) * nl].to(dev)
-            mod = ShardedSupConLoss(tau, sim, lam, 2.0)
+            mod = ShardedSupConLoss(tau, sim, lam, 2.0, exchange=exchange)
             mod.assume_unit_rows = True
             loss = mod(zl, yl, topk_neg=k, alpha=alpha)
             (1.5 * loss).backward()
@@ -75,16 +77,30 @@ def _rank_loss_and_grad(rank, world, port, out):
             (1.5 * loss2).backward()
             torch.cuda.synchronize()
             assert float(loss2) == float(loss) and torch.equal(zl2.grad, zl.grad), name
-        # no gradient wanted: forward only, loss identical
-        with torch.no_grad():
+        # no gradient wanted: forward only, loss identical; then the module keeps working (peer: step closed)
+        for exchange in ("nccl", "peer"):
             name, n, dt, sim, tau, lam, k, alpha, kind, classes = CASES[0]
             x, y = O.make_inputs(n, 256, kind, classes=classes)
             z = F.normalize(x, dim=1).to(torch.bfloat16)
             nl = n // world
-            mod = ShardedSupConLoss(tau, sim, lam, 2.0)
+            mod = ShardedSupConLoss(tau, sim, lam, 2.0, exchange=exchange)
             mod.assume_unit_rows = True
-            l0 = mod(z[rank * nl:(rank + 1) * nl].to(dev), y[rank * nl:(rank + 1) * nl].to(dev), topk_neg=k, alpha=alpha)
-            res["no_grad"] = (float(l0), res[name][0], 0.0)
+            zl, yl = z[rank * nl:(rank + 1) * nl].to(dev), y[rank * nl:(rank + 1) * nl].to(dev)
+            with torch.no_grad():
+                l0 = mod(zl, yl, topk_neg=k, alpha=alpha)
+                l1 = mod(zl, yl, topk_neg=k, alpha=alpha)
+            zg = zl.clone().requires_grad_(True)
+            l2 = mod(zg, yl, topk_neg=k, alpha=alpha)
+            if exchange == "peer":      # a second forward before the pending backward is refused, not silently wrong
+                try:
+                    mod(zg, yl, topk_neg=k, alpha=alpha)
+                    res["peer_guard"] = "no error"
+                except RuntimeError as exc:
+                    res["peer_guard"] = str(exc)
+            l2.backward()
+            torch.cuda.synchronize()
+            assert float(l0) == float(l1) == float(l2)
+            res[f"no_grad/{exchange}"] = (float(l0), res[f"{name}/{exchange}"][0], 0.0)
         # ragged shards raise on every rank instead of hanging the collective
         try:
             m = 64 + 16 * rank
@@ -103,15 +119,19 @@ def test_two_ranks_nccl_loss_and_gradient_vs_oracle():
     mp.spawn(_rank_loss_and_grad, args=(WORLD, _free_port(), out), nprocs=WORLD, join=True)
     for rank in range(WORLD):
         res = out[rank]
-        for (name, n, dt, *_rest) in CASES:
-            loss, want, err = res[name]
-            tol = 2e-3 if dt == "bf16" else 1e-5
-            assert loss == pytest.approx(want, rel=tol), (rank, name)
-            assert err < (3 * tol if dt == "bf16" else tol), (rank, name, err)     # bf16: dz rounded to bf16 by autograd
-        assert res["no_grad"][0] == res["no_grad"][1]
+        for exchange in ("nccl", "peer"):
+            for (name, n, dt, *_rest) in CASES:
+                loss, want, err = res[f"{name}/{exchange}"]
+                tol = 2e-3 if dt == "bf16" else 1e-5
+                assert loss == pytest.approx(want, rel=tol), (rank, name, exchange)
+                assert err < (3 * tol if dt == "bf16" else tol), (rank, name, exchange, err)   # bf16 dz rounded by autograd
+            assert res[f"no_grad/{exchange}"][0] == res[f"no_grad/{exchange}"][1]
+        assert "before the backward" in res["peer_guard"]
         assert "same local batch size" in res["ragged"]
-    for (name, *_r) in CASES:                                                      # identical scalar on both ranks
-        assert out[0][name][0] == out[1][name][0], name
+    for (name, *_r) in CASES:       # identical scalar on both ranks; the two exchanges differ only in summation order
+        assert out[0][f"{name}/nccl"][0] == out[1][f"{name}/nccl"][0], name
+        assert out[0][f"{name}/peer"][0] == out[1][f"{name}/peer"][0], name
+        assert out[0][f"{name}/peer"][0] == pytest.approx(out[0][f"{name}/nccl"][0], rel=1e-6), name
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -141,7 +161,7 @@ def _loader(sampler, feats, labels):
     return [(feats[idx], labels[idx]) for idx in map(torch.tensor, sampler)]
 
 
-def _rank_train(rank, world, port, out):
+def _rank_train(rank, world, port, out, exchange="nccl"):
     import torch.distributed as dist
     from wav2vec_contr_loss_b200 import stage1 as S
     from wav2vec_contr_loss_b200.distributed import ShardedSupConLoss
@@ -153,7 +173,7 @@ def _rank_train(rank, world, port, out):
         head, feats, labels, dataset = _problem()
         head = head.to(dev)
         sampler = S.BalancedBatchSampler(dataset, N_LOCAL, seed=5, rank=rank, world_size=world)
-        loss_fn = ShardedSupConLoss(0.2, "cosine", 0.05, 2.0)
+        loss_fn = ShardedSupConLoss(0.2, "cosine", 0.05, 2.0, exchange=exchange)
         opt = torch.optim.SGD(head.parameters(), lr=0.5)
         history = []
         for epoch in (1, 2):
@@ -167,12 +187,13 @@ def _rank_train(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_ranks_nccl_train_like_one_process_on_the_global_batch(cuda_device):
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_two_ranks_nccl_train_like_one_process_on_the_global_batch(cuda_device, exchange):
     _need_two_gpus()
     from wav2vec_contr_loss_b200 import SupConBinaryLoss
     from wav2vec_contr_loss_b200 import stage1 as S
     out = mp.Manager().dict()
-    mp.spawn(_rank_train, args=(WORLD, _free_port(), out), nprocs=WORLD, join=True)
+    mp.spawn(_rank_train, args=(WORLD, _free_port(), out, exchange), nprocs=WORLD, join=True)
 
     head, feats, labels, dataset = _problem()
     head = head.to(cuda_device)

@@ -22,8 +22,11 @@ try:
     t = sm.empty((65536, 256), dtype=torch.bfloat16, device=dev)
     h = sm.rendezvous(t, dist.group.WORLD)
     out["buffer_ptrs"] = len(h.buffer_ptrs)
-    out["multicast"] = bool(getattr(h, "has_multicast_support", lambda *a: False)(dev.type, dev.index)) \
-        if callable(getattr(h, "has_multicast_support", None)) else None
+    try:
+        from torch._C._autograd import DeviceType
+        out["multicast"] = bool(type(h).has_multicast_support(DeviceType.CUDA, dev.index))
+    except Exception as exc:  # noqa: BLE001
+        out["multicast"] = f"{type(exc).__name__}"
     out["multicast_ptr"] = int(getattr(h, "multicast_ptr", 0) or 0) != 0
     out["signal_pad_bytes"] = int(h.signal_pad_size)
     t.zero_()

@@ -15,6 +15,7 @@ F32, BF16 = 0, 1
 COSINE, GEODESIC = 0, 1
 FLAG_FORCE_EXACT, FLAG_FORCE_TENSOR, FLAG_NO_SMALL = 1, 2, 4
 FLAG_UNIT_ROWS = 32
+FLAG_PEER_EXCHANGE = 64
 STATS_STRIDE = 8
 N_PARTIALS = 8
 P_SUM_FULL, P_CNT_FULL, P_SUM_MINED, P_CNT_MINED, P_SUM_W, P_GCNT_FULL, P_GCNT_MINED, P_FIXMAX = range(8)
@@ -27,6 +28,7 @@ EXPORTS = (
     "supcon_normalize_backward", "supcon_topk_indices", "supcon_forward_rows_local",
     "supcon_forward_rows_remote", "supcon_head_pool_forward", "supcon_head_pool_backward",
     "supcon_finalize_sets", "supcon_backward_rows_local", "supcon_backward_rows_remote",
+    "supcon_peer_push", "supcon_peer_wait", "supcon_peer_end_step",
 )
 
 
@@ -37,6 +39,19 @@ class Problem(ctypes.Structure):
         ("z_dtype", c_int32), ("similarity", c_int32), ("topk", c_int32), ("flags", c_uint32),
         ("tau", c_float), ("alpha", c_float), ("lambda_uni", c_float), ("uni_t", c_float),
     ]
+
+
+class Peer(ctypes.Structure):
+    """struct supcon_peer (include/supcon_b200.h)."""
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("peer_bases", c_void_p), ("off_flags", ctypes.c_uint64),
+                ("epoch", c_void_p)]
+
+
+PEER_FLAG_Z, PEER_FLAG_STATS, PEER_FLAG_DONE, PEER_NFLAGS = 0, 1, 2, 3
+
+
+def peer_flag_bytes(world: int) -> int:
+    return (PEER_NFLAGS * world + 4) * 4
 
 
 _lib = None
@@ -98,6 +113,14 @@ def load():
     lib.supcon_head_pool_backward.restype = c_int32
     lib.supcon_head_pool_backward.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float,
                                               c_void_p, c_void_p, c_void_p, c_void_p]
+    PP = POINTER(Peer)
+    lib.supcon_peer_push.restype = c_int32
+    lib.supcon_peer_push.argtypes = [PP, c_void_p, c_size_t, ctypes.c_uint64, c_void_p, c_size_t, ctypes.c_uint64,
+                                     c_int32, c_int32, c_int32, c_void_p]
+    lib.supcon_peer_wait.restype = c_int32
+    lib.supcon_peer_wait.argtypes = [PP, c_int32, c_void_p]
+    lib.supcon_peer_end_step.restype = c_int32
+    lib.supcon_peer_end_step.argtypes = [PP, c_int32, c_void_p]
     if lib.supcon_abi_version() != ABI_VERSION:
         raise RuntimeError("libsupcon_b200.so ABI version mismatch")
     _lib = lib

@@ -440,6 +440,38 @@ int supcon_head_pool_backward(const float* hs, int32_t batch, int32_t layers, in
   return 0;
 }
 
+int supcon_peer_push(const supcon_peer_t* pe, const void* src0, size_t bytes0, uint64_t dst_off0, const void* src1,
+                     size_t bytes1, uint64_t dst_off1, int32_t flag_id, int32_t wait_flag_id, int32_t include_self,
+                     void* stream) {
+  const char* err = "";
+  if (int rc = peer_check(pe, &err)) return fail(rc, "supcon_peer_push: %s", err);
+  if (!src0 || (bytes0 % 4) || (src1 && (bytes1 % 4)) || flag_id < 0 || flag_id >= SUPCON_PEER_NFLAGS ||
+      wait_flag_id >= SUPCON_PEER_NFLAGS)
+    return fail(SUPCON_E_INVALID, "bad arguments to supcon_peer_push");
+  cudaError_t e = peer_push(*pe, src0, bytes0, dst_off0, src1, bytes1, dst_off1, flag_id, wait_flag_id, include_self,
+                            reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "peer_push_kernel");
+  return 0;
+}
+
+int supcon_peer_wait(const supcon_peer_t* pe, int32_t flag_id, void* stream) {
+  const char* err = "";
+  if (int rc = peer_check(pe, &err)) return fail(rc, "supcon_peer_wait: %s", err);
+  if (flag_id < 0 || flag_id >= SUPCON_PEER_NFLAGS) return fail(SUPCON_E_INVALID, "bad flag id");
+  cudaError_t e = peer_wait(*pe, flag_id, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "peer_wait_kernel");
+  return 0;
+}
+
+int supcon_peer_end_step(const supcon_peer_t* pe, int32_t flag_id, void* stream) {
+  const char* err = "";
+  if (int rc = peer_check(pe, &err)) return fail(rc, "supcon_peer_end_step: %s", err);
+  if (flag_id < 0 || flag_id >= SUPCON_PEER_NFLAGS) return fail(SUPCON_E_INVALID, "bad flag id");
+  cudaError_t e = peer_end_step(*pe, flag_id, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "peer_end_step_kernel");
+  return 0;
+}
+
 int supcon_topk_indices(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all,
                         const float* row_stats, int32_t* idx_out, void* stream) {
   if (int rc = validate(p)) return rc;

@@ -122,6 +122,14 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
                 const double* partials, const float* grad_out, void* dz_out, int dz_dtype, void* workspace,
                 cudaStream_t stream, const char** err, int phase = 0);
 
+// ---- exchange through peer memory (supcon_peer.cu) ----
+int peer_check(const supcon_peer_t* pe, const char** err);
+cudaError_t peer_push(const supcon_peer_t& pe, const void* src0, size_t bytes0, uint64_t off0, const void* src1,
+                      size_t bytes1, uint64_t off1, int flag_id, int wait_flag_id, int include_self,
+                      cudaStream_t stream);
+cudaError_t peer_wait(const supcon_peer_t& pe, int flag_id, cudaStream_t stream);
+cudaError_t peer_end_step(const supcon_peer_t& pe, int flag_id, cudaStream_t stream);
+
 // ---- single-launch small-batch path (supcon_small.cu) ----
 struct SmallArgs {
   const void* z;

@@ -26,6 +26,7 @@
 // underflow, i.e. while 2 M / tau <= 80; rows that break the promise beyond that (M > tau / 0.025) POISON the
 // result: every exponential becomes NaN and so do the loss and dz -- loud, never silently wrong.  Without the
 // promise such inputs take the exact path (online maximum), which handles any norms.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "supcon_common.cuh"
@@ -669,12 +670,12 @@ struct RowMine {  // the same for this thread's row
   int thr_idx;
 };
 
-template <int SIM, bool UNI, bool MINE, bool MASKED>
-__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], uint32_t (&hw)[16], int gj0, int gi, int lab_r,
+template <int SIM, bool UNI, bool MINE, bool MASKED, int NQ>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[4 * NQ], uint32_t (&hw)[2 * NQ], int gj0, int gi, int lab_r,
                                           float A_r, float B_r, float nrm_r, float cu, float c0, const ColVecs& cv,
                                           const RowMine& rm, const TcBwdArgs& a) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     const int4 lb = *reinterpret_cast<const int4*>(cv.lab + 4 * q);
     const float4 Aj = *reinterpret_cast<const float4*>(cv.A + 4 * q);
     const float4 Bj = *reinterpret_cast<const float4*>(cv.B + 4 * q);
@@ -731,12 +732,15 @@ __device__ __forceinline__ int bwd_col_tile(const TcBwdArgs& a, int ct) {
 
 // Backward: a persistent CTA walks a contiguous range of the flattened (128-row block, 64-column
 // tile) work list.  Per segment Z_I lives in tensor memory (A operand of the S MMAs).  BOTH
-// warpgroups work on EVERY tile, warpgroup w on its 32-column half: pull that half of S(t) into
-// registers, form H(t) and write it back as packed bf16 over the first 16 columns of its own half of
-// the S buffer, from where it is the A operand of dZ += H Z_J (no shared-memory round trip).
-// Halving the columns per warpgroup halves the latency between "S(t) complete" and "H(t) ready" --
-// with alternating whole tiles that latency exceeded the S(t+1) + dZ(t-1) window the tensor pipe
-// can cover and the pipe idled ~28 % of the time (ncu r01).  Tensor-pipe order within a segment:
+// warpgroups work on EVERY tile, in two steps: first on columns 0..31 (warpgroup w: its 16 columns),
+// then on columns 32..63, each step ending with its own barrier: S(t) goes to registers, H(t) is formed and
+// written back as packed bf16 over the first 8 columns of each 16-column group of the same S buffer, from
+// where it is the A operand of dZ += H Z_J (no shared-memory round trip).  The issuer starts the dZ
+// MMAs of the first 32 columns as soon as that half of H exists, so the latency between "S(t) complete"
+// and "first dZ(t) MMA can issue" is roughly halved -- with alternating whole tiles per warpgroup (r01) it
+// exceeded the S(t+1) + dZ(t-1) window the tensor pipe can cover and the pipe idled ~28 % of the time
+// (ncu r01; 32-column S sub-tiles with four buffers were tried: the N = 32 MMAs made the kernel 30 % slower).
+// Tensor-pipe order within a segment:
 // S(0) S(1) dZ(0) S(2) dZ(1) ...; tcgen05.mma executes in issue order, so S(t+2) cannot overwrite
 // the buffer dZ(t) is still reading.  Barriers are indexed by a running tile counter.
 template <int SIM, bool UNI, bool MINE>
@@ -750,8 +754,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   constexpr uint32_t TM_DZ = 0, TM_A = 256, TM_S = 384;  // dZ [0,256) | Z_I [256,384) | S buffers 384 + 64 b
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sZJ = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_sfull[2], bar_hfull[2], bar_done,
-      bar_dzfree, bar_col[RING];
+  __shared__ __align__(8) uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_sfull[2], bar_hfull[2][2],
+      bar_done, bar_dzfree, bar_col[RING];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) int32_t lab_ring[RING][BN];
   __shared__ __align__(16) float colA_ring[RING][BN], colB_ring[RING][BN];
@@ -768,7 +772,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
     ptx::mbar_init(&bar_done, 1);
     ptx::mbar_init(&bar_dzfree, 256);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_hfull[b], 256); }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bar_sfull[b], 1);
+      ptx::mbar_init(&bar_hfull[b][0], 256); ptx::mbar_init(&bar_hfull[b][1], 256);
+    }
     for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
     ptx::fence_mbar_init();
     ptx::tma_prefetch_desc(&tmapJ);
@@ -854,14 +861,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
           if (t >= 1) {
             const int g = g0 + t - 1;
             const int st = g % STAGES, buf = g & 1, buse = g >> 1;
-            ptx::mbar_wait(&bar_hfull[buf], buse & 1);
-            ptx::tc_fence_after_sync();
             const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
 #pragma unroll
             for (int kk = 0; kk < BN / 16; ++kk) {
-              // H(t) columns 16 kk .. 16 kk + 15 as packed bf16: warpgroup (kk >> 1) left them at the start
-              // of its own 32-column half of the S buffer
-              ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + 32 * (kk >> 1) + 8 * (kk & 1),
+              if ((kk & 1) == 0) {   // columns 32 (kk >> 1) .. + 31 of H(t) are ready
+                ptx::mbar_wait(&bar_hfull[buf][kk >> 1], buse & 1);
+                ptx::tc_fence_after_sync();
+              }
+              // H(t) columns 16 kk .. 16 kk + 15 as packed bf16 at the start of their 16-column group
+              ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + 16 * kk,
                           ptx::smem_desc_sw128(b0 + kk * 16 * 128, BOXJ_BYTES, 1024), idesc_dz, (t > 1 || kk > 0));
             }
             ptx::mma_commit(&bar_empty[st]);
@@ -873,7 +881,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       }
     }
   } else {
-    // ===== H warpgroups: both take every tile, warpgroup w its columns 32 w .. 32 w + 31 =====
+    // ===== H warpgroups: both take every tile; step `half` covers columns 32 half .., warpgroup w 16 of them =====
     const int wg = (warp - 2) >> 2;
     const int lrow = 32 * (warp & 3) + lane;
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
@@ -901,26 +909,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
         const int g = g0 + t;
         const int buf = g & 1, buse = g >> 1, slot = g % RING;
         const int col0 = bwd_col_tile(a, ct0 + t) * BN;
-        const uint32_t sbuf = tmem + lane_addr + TM_S + buf * BN + 32 * wg;
+        const uint32_t sbuf = tmem + lane_addr + TM_S + buf * BN + 16 * wg;   // this warpgroup's 16 columns of a half
         ptx::mbar_wait(&bar_col[slot], (g / RING) & 1);
         ptx::mbar_wait(&bar_sfull[buf], buse & 1);
         ptx::tc_fence_after_sync();
-        uint32_t r0[32];
-        ptx::tmem_ld32(sbuf, r0);
+        uint32_t r_lo[16], r_hi[16];
+        ptx::tmem_ld16(sbuf, r_lo);
+        ptx::tmem_ld16(sbuf + 32, r_hi);
         ptx::tmem_ld_wait();
-        uint32_t hw[16];
-        ColVecs cv;
-        cv.lab = lab_ring[slot] + 32 * wg; cv.A = colA_ring[slot] + 32 * wg; cv.B = colB_ring[slot] + 32 * wg;
-        cv.nrm = nrm_ring[UNI ? slot : 0] + 32 * wg;
-        cv.Am = colAm_ring[MINE ? slot : 0] + 32 * wg; cv.thr = thr_ring[MINE ? slot : 0] + 32 * wg;
-        cv.thr_idx = thridx_ring[MINE ? slot : 0] + 32 * wg;
         const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
-        if (masked) bwd_chunk<SIM, UNI, MINE, true>(r0, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv, rm, a);
-        else bwd_chunk<SIM, UNI, MINE, false>(r0, hw, col0 + 32 * wg, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv, rm, a);
-        ptx::tmem_st16(sbuf, hw);            // this half of H(t): 32 bf16 = 16 packed columns over S(t)
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before_sync();
-        ptx::mbar_arrive(&bar_hfull[buf]);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c0l = 32 * half + 16 * wg;      // first column of this step within the tile
+          ColVecs cv;
+          cv.lab = lab_ring[slot] + c0l; cv.A = colA_ring[slot] + c0l; cv.B = colB_ring[slot] + c0l;
+          cv.nrm = nrm_ring[UNI ? slot : 0] + c0l;
+          cv.Am = colAm_ring[MINE ? slot : 0] + c0l; cv.thr = thr_ring[MINE ? slot : 0] + c0l;
+          cv.thr_idx = thridx_ring[MINE ? slot : 0] + c0l;
+          uint32_t hw[8];
+          const uint32_t (&rr)[16] = half ? r_hi : r_lo;
+          if (masked) bwd_chunk<SIM, UNI, MINE, true, 4>(rr, hw, col0 + c0l, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv, rm, a);
+          else bwd_chunk<SIM, UNI, MINE, false, 4>(rr, hw, col0 + c0l, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv, rm, a);
+          ptx::tmem_st8(sbuf + 32 * half, hw);   // 16 bf16 = 8 packed columns over the group's own S columns
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&bar_hfull[buf][half]);
+        }
       }
       // ---- segment epilogue: dZ rows out of TMEM; warpgroup w writes columns 128w..128w+127 ----
       ptx::mbar_wait(&bar_done, seg & 1);
@@ -1059,6 +1073,13 @@ int num_sms() {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+const char* tmap_error(int code, const void* base, int rows) {
+  static thread_local char buf[160];
+  snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d; z = %p must be a 16-byte aligned device "
+           "pointer, %d rows)", code, base, rows);
+  return buf;
+}
+
 }  // namespace
 
 // ---- workspace layout shared by forward and backward ----
@@ -1087,7 +1108,7 @@ TcPlan tc_plan(const supcon_problem_t* p) {
     // an own-column phase runs beside an NCCL all-gather kernel: leave SMs free for its channels (a CTA of
     // these kernels fills an SM, so the collective could not co-reside and the two would serialise)
     // (only when that phase is short, i.e. the rank owns at most a quarter of the columns)
-    const bool small_share = 4 * pl.local_cts <= pl.fwd_col_tiles;
+    const bool small_share = (4 * pl.local_cts <= pl.fwd_col_tiles) && !(p->flags & SUPCON_FLAG_PEER_EXCHANGE);
     pl.fwd_sched_local = make_sched(pl.fwd_row_blocks, pl.local_cts, sms, kn.local_ctas,
                                     small_share ? kn.local_free_sms : 0);
     pl.fwd_sched_remote = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles - pl.local_cts, sms, kn.fwd_ctas);
@@ -1189,8 +1210,8 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
   const TcPlan pl = tc_plan(p);
   char* ws = reinterpret_cast<char*>(workspace);
   CUtensorMap tm;
-  if (make_bf16_rowmajor_tmap(&tm, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 128) != 0) {
-    *err = "cuTensorMapEncodeTiled failed (z must be 16-byte aligned)";
+  if (int trc = make_bf16_rowmajor_tmap(&tm, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 128)) {
+    *err = tmap_error(trc, z_all, p->n_total);
     return SUPCON_E_INVALID;
   }
   cudaError_t e = cudaSuccess;
@@ -1292,8 +1313,8 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   const TcPlan pl = tc_plan(p);
   char* ws = reinterpret_cast<char*>(workspace);
   CUtensorMap tmJ;
-  if (make_bf16_rowmajor_tmap(&tmJ, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 64) != 0) {
-    *err = "cuTensorMapEncodeTiled failed (z must be 16-byte aligned)";
+  if (int trc = make_bf16_rowmajor_tmap(&tmJ, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 64)) {
+    *err = tmap_error(trc, z_all, p->n_total);
     return SUPCON_E_INVALID;
   }
   const bool uni = p->lambda_uni > 0.f;

@@ -29,7 +29,15 @@ inline PFN_encodeTiled get_encode_tiled() {
 inline int make_bf16_rowmajor_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                                    uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode_tiled();
-  if (!enc) return -1;
+  if (!enc) return -1000;
+  // The driver call needs a current context on the calling thread.  A thread that has made no runtime call yet
+  // (PyTorch's autograd worker running this library's backward as its first node) has none: CUresult 201.
+  // cudaFree(0) binds the primary context of the thread's current device; once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(0);
+    ctx_bound = true;
+  }
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
   cuuint32_t box[2] = {64, box_rows};

@@ -67,8 +67,95 @@ _COMM_STREAMS = {}
 def _comm_stream(device) -> "torch.cuda.Stream":
     key = (device.type, device.index)
     if key not in _COMM_STREAMS:
-        _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
     return _COMM_STREAMS[key]
+
+
+class PeerExchange:
+    """Exchange buffer of one (group, local rows, width, dtype) shape in SYMMETRIC memory: every rank maps every
+    other rank's buffer (torch.distributed._symmetric_memory over NVLink / NVSwitch), and the library's own kernels
+    write into the peers' buffers directly (csrc/supcon_peer.cu) -- no NCCL call inside a step.
+
+    Layout per rank (byte offsets, 256-aligned): z_all [N, d] | labels_all [N] i32 | stats_all [N, 8] f32 |
+    partial_sets [world, 8] f64 | flags.  Rank r only ever writes block r of each region (in every buffer).
+    One step = forward (+ its backward); a second forward before the pending backward is refused, because the
+    buffers are what the backward reads."""
+
+    def __init__(self, group, n_local: int, d: int, z_dtype, device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _cabi
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_local, self.d, self.device = n_local, d, device
+        n = n_local * self.world
+        esz = torch.empty((), dtype=z_dtype).element_size()
+        self.row_bytes = d * esz
+
+        def al(x):
+            return (x + 255) // 256 * 256
+        self.off_z = 0
+        self.off_labels = al(n * d * esz)
+        self.off_stats = self.off_labels + al(n * 4)
+        self.off_partials = self.off_stats + al(n * 4 * _cabi.STATS_STRIDE)
+        self.off_flags = self.off_partials + al(self.world * 8 * _cabi.N_PARTIALS)
+        total = self.off_flags + al(_cabi.peer_flag_bytes(self.world))
+        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, self.group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                       # every buffer is zeroed before anybody pushes into it
+        self.peer_bases = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self.epoch = torch.ones(1, dtype=torch.int32, device=device)
+        b = self.buf
+        self.z_all = b[self.off_z:self.off_z + n * d * esz].view(z_dtype).view(n, d)
+        self.labels_all = b[self.off_labels:self.off_labels + n * 4].view(torch.int32)
+        self.stats_all = b[self.off_stats:self.off_stats + n * 4 * _cabi.STATS_STRIDE].view(torch.float32).view(
+            n, _cabi.STATS_STRIDE)
+        self.partial_sets = b[self.off_partials:self.off_partials + self.world * 8 * _cabi.N_PARTIALS].view(
+            torch.float64).view(self.world, _cabi.N_PARTIALS)
+        self.desc = _cabi.Peer(rank=self.rank, world=self.world, peer_bases=self.peer_bases.data_ptr(),
+                               off_flags=self.off_flags, epoch=self.epoch.data_ptr())
+        self.pending = False                      # a forward whose backward has not run yet
+
+    def forward(self, zc, labels_local, prob, kernels, want_grad: bool):
+        """push rows | own-column forward -> wait -> other columns -> push statistics -> wait -> loss."""
+        from . import _cabi
+        if self.pending:
+            raise RuntimeError("ShardedSupConLoss (peer exchange): forward() called again before the backward of the "
+                               "previous call; the exchange buffers hold what that backward reads")
+        r, nl, dev = self.rank, self.n_local, self.device
+        cur, comm = torch.cuda.current_stream(dev), _comm_stream(dev)
+        zb, yb = self.z_all[r * nl:(r + 1) * nl], self.labels_all[r * nl:(r + 1) * nl]
+        zb.copy_(zc)                               # own block of the own buffer: only this rank's kernels read it
+        yb.copy_(labels_local)
+        comm.wait_stream(cur)
+        with torch.cuda.stream(comm):              # rows + labels to every peer, beside the own-column forward
+            Fn.peer_push(self.desc, zb, self.off_z + r * nl * self.row_bytes, yb, self.off_labels + r * nl * 4,
+                         _cabi.PEER_FLAG_Z, wait_flag_id=_cabi.PEER_FLAG_DONE, include_self=False)
+        ws = kernels.forward_rows_local(self.z_all, self.labels_all, prob)
+        cur.wait_stream(comm)
+        Fn.peer_wait(self.desc, _cabi.PEER_FLAG_Z, dev)
+        stats, partials = kernels.forward_rows_remote(self.z_all, self.labels_all, prob, ws)
+        Fn.peer_push(self.desc, stats, self.off_stats + r * nl * 4 * _cabi.STATS_STRIDE, partials,
+                     self.off_partials + r * 8 * _cabi.N_PARTIALS, _cabi.PEER_FLAG_STATS, include_self=True)
+        Fn.peer_wait(self.desc, _cabi.PEER_FLAG_STATS, dev)
+        partials_global, loss = kernels.finalize_sets(prob, self.partial_sets)
+        if want_grad:
+            self.pending = True
+        else:
+            Fn.peer_end_step(self.desc, _cabi.PEER_FLAG_DONE, dev)
+        return partials_global, loss
+
+    def backward(self, partials_global, grad_out, prob, kernels, out_dtype):
+        from . import _cabi
+        if not self.pending:
+            raise RuntimeError("ShardedSupConLoss (peer exchange): backward() without a pending forward (a second "
+                               "backward through the same graph is not supported in this mode)")
+        dz = kernels.backward_rows(self.z_all, self.labels_all, self.stats_all, partials_global, grad_out, prob,
+                                   out_dtype)
+        Fn.peer_end_step(self.desc, _cabi.PEER_FLAG_DONE, self.device)
+        self.pending = False
+        return dz
 
 
 def gather_and_forward(z_local, labels_local, make_prob, group, kernels):
@@ -206,13 +293,24 @@ def check_equal_shards(n_local: int, device, group=None):
 
 class _ShardedSupCon(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z_local, labels_local, cfg, group, kernels):
+    def forward(ctx, z_local, labels_local, cfg, group, kernels, peer=None):
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         zc = Fn.canonical_z(z_local.detach())
         check_equal_shards(zc.size(0), zc.device, group)
 
         def make_prob(n_total, d, row_offset, n_rows):
             return Fn.make_problem(n_total, d, Fn._dtype_id(zc), row_offset=row_offset, n_rows=n_rows, **cfg)
+
+        ctx.peer = None
+        if peer is not None:      # exchange through peer memory: this library's kernels only
+            n_local = zc.size(0)
+            prob = make_prob(n_local * world, zc.size(1), rank * n_local, n_local)
+            want_grad = ctx.needs_input_grad[0]
+            partials, loss = peer.forward(zc, labels_local, prob, kernels, want_grad)
+            if want_grad:
+                ctx.save_for_backward(partials)
+                ctx.peer, ctx.prob, ctx.kernels, ctx.in_dtype, ctx.work_dtype = peer, prob, kernels, z_local.dtype, zc.dtype
+            return Fn._loss_dtype(loss, z_local.dtype)
 
         z_all, labels_all, prob, stats, partials = gather_and_forward(zc, labels_local, make_prob, group, kernels)
         want_grad = ctx.needs_input_grad[0]
@@ -237,6 +335,10 @@ class _ShardedSupCon(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.peer is not None:
+            (partials,) = ctx.saved_tensors
+            dz = ctx.peer.backward(partials, grad_out, ctx.prob, ctx.kernels, ctx.work_dtype)
+            return dz.to(ctx.in_dtype), None, None, None, None, None
         z_all, labels_all, stats_all, partials = ctx.saved_tensors
         if ctx.ws is not None:
             dz = ctx.kernels.backward_rows_remote(z_all, labels_all, stats_all, partials, grad_out, ctx.prob, ctx.ws,
@@ -244,7 +346,7 @@ class _ShardedSupCon(torch.autograd.Function):
             ctx.ws = None
         else:
             dz = ctx.kernels.backward_rows(z_all, labels_all, stats_all, partials, grad_out, ctx.prob, ctx.work_dtype)
-        return dz.to(ctx.in_dtype), None, None, None, None
+        return dz.to(ctx.in_dtype), None, None, None, None, None
 
 
 class ShardedSupConLoss(torch.nn.Module):
@@ -257,7 +359,12 @@ class ShardedSupConLoss(torch.nn.Module):
     backward() through the same graph (retain_graph) recomputes the whole backward."""
 
     def __init__(self, temperature: float = 0.2, similarity: str = "geodesic", uniformity_weight: float = 0.0,
-                 uniformity_t: float = 2.0, group: Optional[dist.ProcessGroup] = None, kernels=None):
+                 uniformity_t: float = 2.0, group: Optional[dist.ProcessGroup] = None, kernels=None,
+                 exchange: str = "nccl"):
+        """``exchange``: "nccl" = all-gathers through torch.distributed (works on any group);
+        "peer" = the library's own kernels write rows and row statistics straight into every peer's buffer over
+        NVLink (symmetric memory; one node with peer access; forward and its backward must alternate);
+        "auto" = "peer" when the symmetric buffer can be set up, else "nccl"."""
         super().__init__()
         self.tau = temperature
         self.similarity = similarity.lower()
@@ -268,6 +375,10 @@ class ShardedSupConLoss(torch.nn.Module):
         self.kernels = kernels if kernels is not None else _CudaKernels
         self.kernel_flags = 0
         self.assume_unit_rows = None   # see SupConBinaryLoss.assume_unit_rows
+        if exchange not in ("nccl", "peer", "auto"):
+            raise ValueError(f"Unknown exchange: {exchange}")
+        self.exchange = exchange
+        self._peers = {}               # (n_local, d, dtype) -> PeerExchange
 
     def forward(self, z: torch.Tensor, labels: torch.Tensor, topk_neg: int = 32, alpha: float = 0.0):
         if not (dist.is_available() and dist.is_initialized()):
@@ -279,4 +390,25 @@ class ShardedSupConLoss(torch.nn.Module):
                    uni_t=self.uni_t, topk=topk_neg, alpha=alpha,
                    flags=self.kernel_flags | Fn.unit_rows_flag(z, sim, self.assume_unit_rows))
         lab = Fn.canonical_labels(labels, z.size(0))
-        return _ShardedSupCon.apply(z, lab, cfg, self.group, self.kernels)
+        peer = None
+        if self.exchange != "nccl" and self.kernels is _CudaKernels:
+            peer = self._peer_for(z)
+            if peer is not None:
+                from . import _cabi
+                cfg["flags"] |= _cabi.FLAG_PEER_EXCHANGE
+        return _ShardedSupCon.apply(z, lab, cfg, self.group, self.kernels, peer)
+
+    def _peer_for(self, z):
+        work_dtype = z.dtype if z.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        key = (z.size(0), z.size(1), work_dtype)
+        if key not in self._peers:
+            check_equal_shards(z.size(0), z.device, self.group)
+            try:
+                self._peers[key] = PeerExchange(self.group, z.size(0), z.size(1), work_dtype, z.device)
+            except Exception as exc:  # noqa: BLE001  (no peer access / symmetric memory unavailable)
+                if self.exchange == "peer":
+                    raise
+                import warnings
+                warnings.warn(f"ShardedSupConLoss: peer exchange unavailable ({type(exc).__name__}: {exc}); using NCCL")
+                self._peers[key] = None
+        return self._peers[key]

@@ -210,6 +210,30 @@ def finalize_sets(prob: _cabi.Problem, partial_sets: torch.Tensor):
     return partials, loss
 
 
+def peer_push(desc: _cabi.Peer, src0: torch.Tensor, dst_off0: int, src1, dst_off1: int, flag_id: int,
+              wait_flag_id: int = -1, include_self: bool = False):
+    """supcon_peer_push: src0 (and src1) -> the same byte offsets of every peer's exchange buffer, then the flag."""
+    lib = _cabi.load()
+    dev = src0.device
+    with torch.cuda.device(dev):
+        _cabi.check(lib.supcon_peer_push(ctypes.byref(desc), _p(src0), src0.numel() * src0.element_size(), int(dst_off0),
+                                         _p(src1), 0 if src1 is None else src1.numel() * src1.element_size(),
+                                         int(dst_off1), int(flag_id), int(wait_flag_id), 1 if include_self else 0,
+                                         _stream(dev)), "supcon_peer_push")
+
+
+def peer_wait(desc: _cabi.Peer, flag_id: int, device):
+    lib = _cabi.load()
+    with torch.cuda.device(device):
+        _cabi.check(lib.supcon_peer_wait(ctypes.byref(desc), int(flag_id), _stream(device)), "supcon_peer_wait")
+
+
+def peer_end_step(desc: _cabi.Peer, flag_id: int, device):
+    lib = _cabi.load()
+    with torch.cuda.device(device):
+        _cabi.check(lib.supcon_peer_end_step(ctypes.byref(desc), int(flag_id), _stream(device)), "supcon_peer_end_step")
+
+
 def backward_rows_local(z_all, labels_i32, stats_local, partials_local, prob: _cabi.Problem) -> torch.Tensor:
     """Phase 1 of the two-phase row-block backward: the rank's own columns, from its own statistics only
     (no exchange needed yet, no grad_out needed yet).  Returns the workspace backward_rows_remote must be given."""
