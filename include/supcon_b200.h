@@ -214,6 +214,16 @@ int supcon_loss_and_grad(const supcon_problem_t* p, const void* z, const int32_t
                          float* loss_out, void* dz_out, int32_t dz_dtype, float* row_stats,
                          double* partials, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Labels of any width -> the int32 class keys the kernels compare (loss.py:123 compares labels with ==; the
+ * callers pass int64, stage1_utils.py:112): equal labels <-> equal keys.  One launch, replaces a dtype cast.
+ * A label that 32 bits cannot hold losslessly (int64 outside int32, float64 that is not a float32) makes the
+ * kernel report the row and trap -- a loud device fault instead of two classes silently merged.  -0.0 == +0.0;
+ * every NaN row gets a key of its own (NaN equals nothing). */
+#define SUPCON_LABEL_I64 1
+#define SUPCON_LABEL_F32 2
+#define SUPCON_LABEL_F64 3
+int supcon_label_keys(const void* labels, int32_t dtype, int32_t n, int32_t* keys_out, void* stream);
+
 /* Row L2 normalisation either side of the loss (stage1_utils.py:123,149):
  *   z = x / max(|x|, 1e-12);   dx = (dz - z (z.dz)) / max(|x|, 1e-12) */
 int supcon_normalize_forward(const float* x, int32_t n, int32_t d, void* z_out, int32_t z_dtype,

@@ -34,6 +34,28 @@ def test_dropout_stream_follows_manual_seed():
     assert a.rng_state.tolist() == [11, 0] and b.rng_state.tolist() == [12, 0]
 
 
+def test_dropout_stream_can_be_reseeded_per_rank_and_checkpointed():
+    """the stream is seeded at construction (documented), reseed() follows a later manual_seed and
+    mixes a per-rank stream id, and its position survives a checkpoint without touching state_dict()."""
+    torch.manual_seed(3)
+    head = FusedCompressionHead(8, 4)
+    torch.manual_seed(99)
+    assert head.rng_state.tolist() == [3, 0]            # construction-time seed: manual_seed afterwards is inert ...
+    head.reseed()
+    assert head.rng_state.tolist() == [99, 0]           # ... until reseed()
+    keys = set()
+    for rank in range(4):
+        head.reseed(seed=1337, stream=rank)
+        keys.add(head.rng_state.tolist()[0])
+    assert len(keys) == 4                               # same torch seed on every rank, different masks
+    head.rng_state[1] = 41
+    saved = head.dropout_stream_state()
+    other = FusedCompressionHead(8, 4)
+    other.load_dropout_stream_state(saved)
+    assert other.rng_state.tolist() == head.rng_state.tolist() and saved[1] == 41
+    assert list(head.state_dict().keys()) == ["mlp3.weight", "mlp3.bias"]
+
+
 def test_no_cpu_path():
     head = FusedCompressionHead(8, 4, 0.0)
     hs = torch.randn(2, 3, 8, 5)

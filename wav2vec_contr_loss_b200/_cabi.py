@@ -14,6 +14,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 F32, BF16 = 0, 1
 COSINE, GEODESIC = 0, 1
 FLAG_FORCE_EXACT, FLAG_FORCE_TENSOR, FLAG_NO_SMALL = 1, 2, 4
+LABEL_I64, LABEL_F32, LABEL_F64 = 1, 2, 3
 FLAG_UNIT_ROWS = 32
 FLAG_PEER_EXCHANGE = 64
 STATS_STRIDE = 8
@@ -28,7 +29,7 @@ EXPORTS = (
     "supcon_normalize_backward", "supcon_topk_indices", "supcon_forward_rows_local",
     "supcon_forward_rows_remote", "supcon_head_pool_forward", "supcon_head_pool_backward",
     "supcon_finalize_sets", "supcon_backward_rows_local", "supcon_backward_rows_remote",
-    "supcon_peer_push", "supcon_peer_wait", "supcon_peer_end_step",
+    "supcon_peer_push", "supcon_peer_wait", "supcon_peer_end_step", "supcon_label_keys",
 )
 
 
@@ -113,6 +114,8 @@ def load():
     lib.supcon_head_pool_backward.restype = c_int32
     lib.supcon_head_pool_backward.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float,
                                               c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.supcon_label_keys.restype = c_int32
+    lib.supcon_label_keys.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p]
     PP = POINTER(Peer)
     lib.supcon_peer_push.restype = c_int32
     lib.supcon_peer_push.argtypes = [PP, c_void_p, c_size_t, ctypes.c_uint64, c_void_p, c_size_t, ctypes.c_uint64,

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <string>
+#include <type_traits>
 
 #include "supcon_common.cuh"
 #include "supcon_internal.h"
@@ -128,6 +129,34 @@ __global__ void finalize_sets_kernel(const double* sets, int n_sets, double* par
   }
   __syncthreads();
   if (k == 0 && loss_out) *loss_out = global_coef(pg, n_total, tau, alpha, lambda_uni, uni_t).loss;
+}
+
+// ---- labels of any width -> int32 class keys: equal labels <-> equal keys (loss.py:123 compares with ==) ----
+// int64 values outside int32 and float64 values that float32 cannot hold exactly cannot be keyed losslessly in 32
+// bits: the kernel reports the row and traps (a loud device-side fault) instead of silently merging two classes.
+// NaN never equals anything in the reference: every NaN row gets a key of its own.
+template <typename T>
+__global__ void label_keys_kernel(const T* __restrict__ in, int n, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T v = in[i];
+  if constexpr (sizeof(T) == 8 && !std::is_floating_point<T>::value) {          // int64
+    if (v != (T)(int32_t)v) {
+      printf("supcon: integer label %lld (row %d) does not fit 32 bits; relabel the classes densely\n", (long long)v, i);
+      __trap();
+    }
+    out[i] = (int32_t)v;
+  } else {                                                                        // float32 / float64
+    float f = (float)v;
+    if constexpr (sizeof(T) == 8) {
+      if (v == v && (double)f != (double)v) {
+        printf("supcon: float64 label %.17g (row %d) is not exactly a float32; relabel the classes\n", (double)v, i);
+        __trap();
+      }
+    }
+    if (f != f) out[i] = 0x7fc00000 | (i & 0x3fffff);     // NaN: matches no other row
+    else out[i] = __float_as_int(f + 0.0f);               // -0.0 == +0.0
+  }
 }
 
 // ---- row L2 normalisation (stage1_utils.py:123,149): one warp per row ----
@@ -361,6 +390,19 @@ int supcon_loss_and_grad(const supcon_problem_t* p, const void* z, const int32_t
     rc = supcon_backward_rows(p, z, labels, row_stats, partials, nullptr, dz_out, dz_dtype, workspace,
                               workspace_bytes, stream);
   return rc;
+}
+
+int supcon_label_keys(const void* labels, int32_t dtype, int32_t n, int32_t* keys_out, void* stream) {
+  if (!labels || !keys_out || n < 1) return fail(SUPCON_E_INVALID, "bad arguments to supcon_label_keys");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = (n + 255) / 256;
+  if (dtype == SUPCON_LABEL_I64) label_keys_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)labels, n, keys_out);
+  else if (dtype == SUPCON_LABEL_F32) label_keys_kernel<float><<<blocks, 256, 0, st>>>((const float*)labels, n, keys_out);
+  else if (dtype == SUPCON_LABEL_F64) label_keys_kernel<double><<<blocks, 256, 0, st>>>((const double*)labels, n, keys_out);
+  else return fail(SUPCON_E_INVALID, "unknown label dtype %d", dtype);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "label_keys_kernel");
+  return 0;
 }
 
 int supcon_normalize_forward(const float* x, int32_t n, int32_t d, void* z_out, int32_t z_dtype,

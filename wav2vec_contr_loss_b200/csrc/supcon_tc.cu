@@ -731,18 +731,19 @@ __device__ __forceinline__ int bwd_col_tile(const TcBwdArgs& a, int ct) {
 }
 
 // Backward: a persistent CTA walks a contiguous range of the flattened (128-row block, 64-column
-// tile) work list.  Per segment Z_I lives in tensor memory (A operand of the S MMAs).  BOTH
-// warpgroups work on EVERY tile, in two steps: first on columns 0..31 (warpgroup w: its 16 columns),
-// then on columns 32..63, each step ending with its own barrier: S(t) goes to registers, H(t) is formed and
-// written back as packed bf16 over the first 8 columns of each 16-column group of the same S buffer, from
-// where it is the A operand of dZ += H Z_J (no shared-memory round trip).  The issuer starts the dZ
-// MMAs of the first 32 columns as soon as that half of H exists, so the latency between "S(t) complete"
-// and "first dZ(t) MMA can issue" is roughly halved -- with alternating whole tiles per warpgroup (r01) it
-// exceeded the S(t+1) + dZ(t-1) window the tensor pipe can cover and the pipe idled ~28 % of the time
-// (ncu r01; 32-column S sub-tiles with four buffers were tried: the N = 32 MMAs made the kernel 30 % slower).
-// Tensor-pipe order within a segment:
+// tile) work list.  Per segment Z_I lives in tensor memory (A operand of the S MMAs); the two
+// warpgroups take alternate tiles: pull S(t) into registers, form H(t) and write it back as packed
+// bf16 over the first 32 columns of the same S buffer, from where it is the A operand of
+// dZ += H Z_J (no shared-memory round trip).  Tensor-pipe order within a segment:
 // S(0) S(1) dZ(0) S(2) dZ(1) ...; tcgen05.mma executes in issue order, so S(t+2) cannot overwrite
 // the buffer dZ(t) is still reading.  Barriers are indexed by a running tile counter.
+// The pipe idles ~25 % of the time because the ld -> exp/H -> st -> barrier chain of one tile (>= 512 XU
+// cycles per SMSP for its 8192 exponentials, ~500 cycles of fixed latencies) is longer than the
+// S(t+1) + dZ(t-1) = 1024 cycles the pipe can cover while the 512 TMEM columns (dZ 256 | Z_I 128 | 2 x 64 S)
+// leave no room for a third S buffer.  Three restructurings were measured in round 2 (A/B in one GPU call,
+// profiles/r02_bwd_restructuring_ab.md) and all LOST to this form: both warpgroups on every tile (32 columns
+// each): +2 %; the same with the dZ MMAs of the first 32 columns issued early: +12 %; 32-column S sub-tiles
+// in four TMEM buffers with dZ lagging three sub-tiles: +30 % (N = 32 MMAs do not run at N = 64 rate).
 template <int SIM, bool UNI, bool MINE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapJ,
                                                              const __nv_bfloat16* __restrict__ z, TcBwdArgs a) {
@@ -754,7 +755,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   constexpr uint32_t TM_DZ = 0, TM_A = 256, TM_S = 384;  // dZ [0,256) | Z_I [256,384) | S buffers 384 + 64 b
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sZJ = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_sfull[2], bar_hfull[2][2],
+  __shared__ __align__(8) uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_sfull[2], bar_hfull[2],
       bar_done, bar_dzfree, bar_col[RING];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) int32_t lab_ring[RING][BN];
@@ -772,10 +773,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
     ptx::mbar_init(&bar_done, 1);
     ptx::mbar_init(&bar_dzfree, 256);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&bar_sfull[b], 1);
-      ptx::mbar_init(&bar_hfull[b][0], 256); ptx::mbar_init(&bar_hfull[b][1], 256);
-    }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_hfull[b], 128); }
     for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
     ptx::fence_mbar_init();
     ptx::tma_prefetch_desc(&tmapJ);
@@ -861,15 +859,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
           if (t >= 1) {
             const int g = g0 + t - 1;
             const int st = g % STAGES, buf = g & 1, buse = g >> 1;
+            ptx::mbar_wait(&bar_hfull[buf], buse & 1);
+            ptx::tc_fence_after_sync();
             const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
 #pragma unroll
             for (int kk = 0; kk < BN / 16; ++kk) {
-              if ((kk & 1) == 0) {   // columns 32 (kk >> 1) .. + 31 of H(t) are ready
-                ptx::mbar_wait(&bar_hfull[buf][kk >> 1], buse & 1);
-                ptx::tc_fence_after_sync();
-              }
-              // H(t) columns 16 kk .. 16 kk + 15 as packed bf16 at the start of their 16-column group
-              ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + 16 * kk,
+              ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + 8 * kk,
                           ptx::smem_desc_sw128(b0 + kk * 16 * 128, BOXJ_BYTES, 1024), idesc_dz, (t > 1 || kk > 0));
             }
             ptx::mma_commit(&bar_empty[st]);
@@ -881,12 +876,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       }
     }
   } else {
-    // ===== H warpgroups: both take every tile; step `half` covers columns 32 half .., warpgroup w 16 of them =====
+    // ===== H warpgroups: warpgroup w takes the tiles with (running index & 1) == w (S/H buffer w) =====
     const int wg = (warp - 2) >> 2;
     const int lrow = 32 * (warp & 3) + lane;
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     const float cu = UNI ? a.scalars[0] : 0.f;
     const float c0 = a.scalars[1];   // -M/tau * log2(e), M = the forward's fixed maximum
+    const uint32_t sbuf = tmem + lane_addr + TM_S + wg * BN;
     int g0 = 0, seg = 0;
     for (long long u = u_begin; u < u_end; ++seg) {
       const int rb = (int)(u / sc.T), ct0 = (int)(u % sc.T);
@@ -905,36 +901,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       const float nrm_r = UNI ? a.nrm_pad[gic] : 0.f;
       RowMine rm;
       rm.Am = MINE ? a.colAm[gic] : 0.f; rm.thr = MINE ? a.colThr[gic] : 0.f; rm.thr_idx = MINE ? a.colThrIdx[gic] : 0;
-      for (int t = 0; t < nt; ++t) {
+      for (int t = ((g0 & 1) == wg ? 0 : 1); t < nt; t += 2) {
         const int g = g0 + t;
-        const int buf = g & 1, buse = g >> 1, slot = g % RING;
+        const int buse = g >> 1, slot = g % RING;
         const int col0 = bwd_col_tile(a, ct0 + t) * BN;
-        const uint32_t sbuf = tmem + lane_addr + TM_S + buf * BN + 16 * wg;   // this warpgroup's 16 columns of a half
         ptx::mbar_wait(&bar_col[slot], (g / RING) & 1);
-        ptx::mbar_wait(&bar_sfull[buf], buse & 1);
+        ptx::mbar_wait(&bar_sfull[wg], buse & 1);
         ptx::tc_fence_after_sync();
-        uint32_t r_lo[16], r_hi[16];
-        ptx::tmem_ld16(sbuf, r_lo);
-        ptx::tmem_ld16(sbuf + 32, r_hi);
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld32(sbuf, r0);
+        ptx::tmem_ld32(sbuf + 32, r1);
         ptx::tmem_ld_wait();
+        uint32_t hw[32];
+        uint32_t (&h0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[0]);
+        uint32_t (&h1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[16]);
+        ColVecs cv0, cv1;
+        cv0.lab = lab_ring[slot]; cv0.A = colA_ring[slot]; cv0.B = colB_ring[slot]; cv0.nrm = nrm_ring[UNI ? slot : 0];
+        cv0.Am = colAm_ring[MINE ? slot : 0]; cv0.thr = thr_ring[MINE ? slot : 0]; cv0.thr_idx = thridx_ring[MINE ? slot : 0];
+        cv1.lab = cv0.lab + 32; cv1.A = cv0.A + 32; cv1.B = cv0.B + 32; cv1.nrm = cv0.nrm + 32;
+        cv1.Am = cv0.Am + 32; cv1.thr = cv0.thr + 32; cv1.thr_idx = cv0.thr_idx + 32;
         const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int c0l = 32 * half + 16 * wg;      // first column of this step within the tile
-          ColVecs cv;
-          cv.lab = lab_ring[slot] + c0l; cv.A = colA_ring[slot] + c0l; cv.B = colB_ring[slot] + c0l;
-          cv.nrm = nrm_ring[UNI ? slot : 0] + c0l;
-          cv.Am = colAm_ring[MINE ? slot : 0] + c0l; cv.thr = thr_ring[MINE ? slot : 0] + c0l;
-          cv.thr_idx = thridx_ring[MINE ? slot : 0] + c0l;
-          uint32_t hw[8];
-          const uint32_t (&rr)[16] = half ? r_hi : r_lo;
-          if (masked) bwd_chunk<SIM, UNI, MINE, true, 4>(rr, hw, col0 + c0l, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv, rm, a);
-          else bwd_chunk<SIM, UNI, MINE, false, 4>(rr, hw, col0 + c0l, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv, rm, a);
-          ptx::tmem_st8(sbuf + 32 * half, hw);   // 16 bf16 = 8 packed columns over the group's own S columns
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(&bar_hfull[buf][half]);
+        if (masked) {
+          bwd_chunk<SIM, UNI, MINE, true, 8>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv0, rm, a);
+          bwd_chunk<SIM, UNI, MINE, true, 8>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv1, rm, a);
+        } else {
+          bwd_chunk<SIM, UNI, MINE, false, 8>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv0, rm, a);
+          bwd_chunk<SIM, UNI, MINE, false, 8>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv1, rm, a);
         }
+        ptx::tmem_st32(sbuf, hw);            // H(t): 64 bf16 = 32 packed columns over S(t)
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(&bar_hfull[wg]);
       }
       // ---- segment epilogue: dZ rows out of TMEM; warpgroup w writes columns 128w..128w+127 ----
       ptx::mbar_wait(&bar_done, seg & 1);

@@ -55,16 +55,41 @@ def canonical_z(z: torch.Tensor) -> torch.Tensor:
 
 
 def canonical_labels(labels: torch.Tensor, n: int) -> torch.Tensor:
-    """int32 class keys: equal labels <-> equal keys (reference compares with ==,
-    loss.py:123-124; any dtype, shape (B,) or (B,1))."""
+    """int32 class keys: equal labels <-> equal keys (reference compares with ==, loss.py:123-124; any dtype,
+    shape (B,) or (B,1)).  Wide labels (int64 as the callers pass them, float32/64) go through ONE kernel of the
+    library (supcon_label_keys) that also guards the narrowing: a label 32 bits cannot hold losslessly is a loud
+    device fault, never two classes silently merged; NaN labels match nothing, as in the reference."""
     lab = labels.reshape(-1)
     if lab.numel() != n:
         raise ValueError(f"labels must have {n} elements, got {lab.numel()}")
-    if lab.is_floating_point():
-        lab = (lab.float() + 0.0).contiguous().view(torch.int32)   # -0.0 -> +0.0, then bit pattern
-    else:
-        lab = lab.to(torch.int32)
-    return lab.contiguous()
+    if lab.dtype == torch.int32:
+        return lab.contiguous()
+    if lab.dtype in (torch.int8, torch.int16, torch.uint8, torch.bool):
+        return lab.to(torch.int32).contiguous()                     # lossless
+    if lab.dtype in (torch.float16, torch.bfloat16):
+        lab = lab.float()                                           # lossless
+    code = {torch.int64: _cabi.LABEL_I64, torch.float32: _cabi.LABEL_F32, torch.float64: _cabi.LABEL_F64}.get(lab.dtype)
+    if code is None:
+        raise TypeError(f"unsupported label dtype {lab.dtype}")
+    lab = lab.contiguous()
+    if not lab.is_cuda:   # host tensors only occur with the CPU stand-in kernels of the tests: same rules, eagerly
+        if lab.dtype == torch.int64:
+            if n and (int(lab.max()) > 2**31 - 1 or int(lab.min()) < -2**31):
+                raise ValueError("integer labels do not fit 32 bits; relabel the classes densely")
+            return lab.to(torch.int32)
+        f = lab.float()
+        if lab.dtype == torch.float64 and not bool(((f.double() == lab) | lab.isnan()).all()):
+            raise ValueError("float64 labels are not exactly float32 values; relabel the classes")
+        keys = (f + 0.0).view(torch.int32).clone()
+        nan = f.isnan()
+        keys[nan] = 0x7fc00000 | (torch.arange(n, dtype=torch.int32)[nan] & 0x3fffff)
+        return keys
+    lib = _cabi.load()
+    dev = lab.device
+    with torch.cuda.device(dev):
+        keys = torch.empty(n, dtype=torch.int32, device=dev)
+        _cabi.check(lib.supcon_label_keys(_p(lab), code, n, _p(keys), _stream(dev)), "supcon_label_keys")
+    return keys
 
 
 _PROBLEMS = {}          # argument tuple -> Problem (host structs are immutable once built: safe to share)

@@ -92,9 +92,38 @@ class FusedCompressionHead(nn.Module):
         self.dropout_head = nn.Dropout(p=dropout_rate)
         self.activation_head = nn.LeakyReLU()
         self.mlp3 = nn.Linear(input_dim, hidden_dim)
-        # {seed, offset} of the dropout stream, on the device so that CUDA-graph replays draw fresh masks
-        seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF      # follows torch.manual_seed, like nn.Dropout's stream
-        self.register_buffer("rng_state", torch.tensor([seed, 0], dtype=torch.int64), persistent=False)
+        # {seed, offset} of the dropout stream, on the device so that CUDA-graph replays draw fresh masks.
+        # Seeded HERE, at construction, from torch.initial_seed() (a later torch.manual_seed() does not move it:
+        # call reseed()).  dropout_stream_state() / load_dropout_stream_state() let a resumed run continue the
+        # stream instead of replaying the masks from offset 0.
+        self.register_buffer("rng_state", torch.tensor([0, 0], dtype=torch.int64), persistent=False)
+        self.reseed()
+
+    def reseed(self, seed=None, stream=None) -> None:
+        """Restart the dropout stream.  ``seed`` defaults to ``torch.initial_seed()``; ``stream`` (default: this
+        process's rank in the default process group, 0 without one) is mixed into the key so that the ranks of a
+        data-parallel job -- which the reference's set_seed() gives the SAME torch seed -- draw different masks."""
+        if seed is None:
+            seed = torch.initial_seed()
+        if stream is None:
+            import torch.distributed as dist
+            stream = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+        key = (int(seed) ^ (int(stream) * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF
+        with torch.no_grad():
+            self.rng_state.copy_(torch.tensor([key, 0], dtype=torch.int64))
+
+    # -- checkpointing.  state_dict() stays exactly the reference module's (mlp3.weight, mlp3.bias) so that
+    #    checkpoints move both ways between this class and compression_module.CompressionModule with strict=True;
+    #    the position of the dropout stream is saved NEXT to it, like an optimizer's state:
+    #        ckpt = {"compression_state_dict": head.state_dict(), "dropout_stream": head.dropout_stream_state()}
+    def dropout_stream_state(self):
+        """{seed key, offset} of the dropout stream as Python ints (one device read)."""
+        return [int(v) for v in self.rng_state.tolist()]
+
+    def load_dropout_stream_state(self, state) -> None:
+        """Continue the stream of a saved run instead of replaying its masks from offset 0."""
+        with torch.no_grad():
+            self.rng_state.copy_(torch.tensor([int(state[0]), int(state[1])], dtype=torch.int64))
 
     def pooled_features(self, hs: torch.Tensor) -> torch.Tensor:
         """(B, F): mean over time of the activated layer mean."""
