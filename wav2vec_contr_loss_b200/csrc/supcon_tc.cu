@@ -264,25 +264,31 @@ __device__ __forceinline__ void coop_insert(float* wl_v, int* wl_i, int lane, in
   if (lane == L) { ms.cnt = newcnt; ms.thr = newthr; }
 }
 
-// Hard-negative candidates of one 32-column chunk, handled after the chunk's arithmetic, in column
+// Hard-negative candidates of one 32-column chunk are handled after the chunk's arithmetic, in column
 // order, re-checked against the row's CURRENT K-th value (the same decisions as an element-by-element
-// scan).  Kept out of line and compact: inlining it 32x per chunk made the hot loop miss the
-// instruction cache (forward 12x slower).  The similarity of a flagged column is re-read from tensor
-// memory (the S buffer is released only after the tile's candidates are done when mining).
-__device__ __noinline__ MineState mine_candidates(int sim, uint32_t taddr_chunk, unsigned anyc, unsigned cmask, int gj0,
-                                                  float* wl_v, int* wl_i, int lane, int K, MineState ms) {
-  while (anyc) {
-    const int e = __ffs(anyc) - 1;
-    anyc &= anyc - 1;
-    const float c = __uint_as_float(ptx::tmem_ld1(taddr_chunk + e));
-    ptx::tmem_ld_wait();
-    const float s = (sim == SUPCON_GEODESIC) ? geodesic_sim_fast(c) : c;
-    unsigned cands = __ballot_sync(0xffffffffu, ((cmask >> e) & 1u) && s > ms.thr);
-    while (cands) {
-      const int L = __ffs(cands) - 1;
-      cands &= cands - 1;
-      coop_insert(wl_v, wl_i, lane, L, __shfl_sync(0xffffffffu, s, L), gj0 + e, K, ms);
-    }
+// scan).  The similarity of a flagged column e (warp-uniform) is picked out of the chunk's registers by a
+// uniform switch -- not re-read from tensor memory as in round 1 -- so the S buffer is released as soon as
+// the tile is in registers and the next MMA overlaps the exp work exactly as without mining.  The sorted
+// insert itself stays out of line and compact: inlining it 32x per chunk made the hot loop miss the
+// instruction cache (forward 12x slower).
+__device__ __forceinline__ uint32_t reg_select(const uint32_t (&r)[32], int e) {
+  uint32_t v = 0;
+  switch (e) {
+#define SUPCON_SEL(i) case i: v = r[i]; break;
+    SUPCON_SEL(0) SUPCON_SEL(1) SUPCON_SEL(2) SUPCON_SEL(3) SUPCON_SEL(4) SUPCON_SEL(5) SUPCON_SEL(6) SUPCON_SEL(7)
+    SUPCON_SEL(8) SUPCON_SEL(9) SUPCON_SEL(10) SUPCON_SEL(11) SUPCON_SEL(12) SUPCON_SEL(13) SUPCON_SEL(14) SUPCON_SEL(15)
+    SUPCON_SEL(16) SUPCON_SEL(17) SUPCON_SEL(18) SUPCON_SEL(19) SUPCON_SEL(20) SUPCON_SEL(21) SUPCON_SEL(22) SUPCON_SEL(23)
+    SUPCON_SEL(24) SUPCON_SEL(25) SUPCON_SEL(26) SUPCON_SEL(27) SUPCON_SEL(28) SUPCON_SEL(29) SUPCON_SEL(30) SUPCON_SEL(31)
+#undef SUPCON_SEL
+  }
+  return v;
+}
+__device__ __noinline__ MineState insert_candidates(unsigned cands, float s, int gj, float* wl_v, int* wl_i, int lane,
+                                                    int K, MineState ms) {
+  while (cands) {
+    const int L = __ffs(cands) - 1;
+    cands &= cands - 1;
+    coop_insert(wl_v, wl_i, lane, L, __shfl_sync(0xffffffffu, s, L), gj, K, ms);
   }
   return ms;
 }
@@ -333,9 +339,17 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
     }
   }
   if (MINE) {
-    const unsigned anyc = __reduce_or_sync(0xffffffffu, cmask);
-    if (anyc) ms = mine_candidates(SIM, taddr_chunk, anyc, cmask, gj0, wl_v, wl_i, lane, K, ms);
+    unsigned anyc = __reduce_or_sync(0xffffffffu, cmask);
+    while (anyc) {
+      const int e = __ffs(anyc) - 1;
+      anyc &= anyc - 1;
+      const float c = __uint_as_float(reg_select(r, e));
+      const float s = (SIM == SUPCON_GEODESIC) ? geodesic_sim_fast(c) : c;
+      const unsigned cands = __ballot_sync(0xffffffffu, ((cmask >> e) & 1u) && s > ms.thr);
+      if (cands) ms = insert_candidates(cands, s, gj0 + e, wl_v, wl_i, lane, K, ms);
+    }
   }
+  (void)taddr_chunk;
 }
 
 // logical column tile of this launch -> physical tile: a launch covers [ct_base, ...) minus an excluded window
@@ -504,10 +518,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
         ptx::tmem_ld32(taddr + 64, r2);
         ptx::tmem_ld32(taddr + 96, r3);
         ptx::tmem_ld_wait();
-        if (!MINE) {
-          ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(&bar_tempty[wg]);   // S_g is free again: the next MMA overlaps the work below
-        }
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(&bar_tempty[wg]);   // S_g is free again: the next MMA overlaps the work below
         const bool masked = (col0 + BN > a.n_total) || (col0 < rblk0 + TBM && rblk0 < col0 + BN);
         const int32_t* lab_s = lab_ring[slot];
         const float* nrm_s = nrm_ring[UNI ? slot : 0];
@@ -521,10 +533,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
           fwd_chunk<SIM, UNI, MINE, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
           fwd_chunk<SIM, UNI, MINE, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
           fwd_chunk<SIM, UNI, MINE, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
-        }
-        if (MINE) {   // candidates re-read S from tensor memory: release the buffer only now
-          ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(&bar_tempty[wg]);
         }
       }
       if (gi < a.row_offset + a.n_rows) {
@@ -740,10 +748,14 @@ __device__ __forceinline__ int bwd_col_tile(const TcBwdArgs& a, int ct) {
 // The pipe idles ~25 % of the time because the ld -> exp/H -> st -> barrier chain of one tile (>= 512 XU
 // cycles per SMSP for its 8192 exponentials, ~500 cycles of fixed latencies) is longer than the
 // S(t+1) + dZ(t-1) = 1024 cycles the pipe can cover while the 512 TMEM columns (dZ 256 | Z_I 128 | 2 x 64 S)
-// leave no room for a third S buffer.  Three restructurings were measured in round 2 (A/B in one GPU call,
-// profiles/r02_bwd_restructuring_ab.md) and all LOST to this form: both warpgroups on every tile (32 columns
+// leave no room for a third S buffer.  Four restructurings were measured in round 2 (A/B in one GPU call each,
+// profiles/r02_bwd_restructuring_ab.md) and none beat this form: both warpgroups on every tile (32 columns
 // each): +2 %; the same with the dZ MMAs of the first 32 columns issued early: +12 %; 32-column S sub-tiles
-// in four TMEM buffers with dZ lagging three sub-tiles: +30 % (N = 32 MMAs do not run at N = 64 rate).
+// in four TMEM buffers with dZ lagging three sub-tiles: +30 % (N = 32 MMAs do not run at N = 64 rate); this
+// form with H published in two halves (dZ of columns 0..31 issued early): +-0 % -- so the H latency is not
+// what holds the pipe at ~75 %.  What the variants share is the shared-memory traffic per tile: 32 KB read by
+// the S MMAs + 32 KB by the dZ MMAs + 32 KB written by TMA = 94 B/clk of the 128 B/clk port; sharing Z_J
+// between two CTAs (cta_group::2) is the remaining lever.
 template <int SIM, bool UNI, bool MINE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapJ,
                                                              const __nv_bfloat16* __restrict__ z, TcBwdArgs a) {
