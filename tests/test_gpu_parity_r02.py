@@ -313,3 +313,39 @@ def test_duplicate_rows_with_uniformity(cuda_device, family, sim):
         keep &= ~dup
         assert int(keep.sum()) > n // 2
         assert G.rel_err(dz[keep], ref["dz"][keep]) < (50 * tol if dtype == torch.float32 else 3 * tol)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# single-launch kernel for mid-size batches, 160 < N <= 512 (supcon_mid.cu): the reference's default batch (256)
+# ---------------------------------------------------------------------------------------------------------
+MID_CASES = [
+    # n, d, kind, classes, sim, tau, lam, K, alpha
+    (256, 256, "iso", 2, "cosine", 0.07, 0.0, 15, 0.0),          # stage1_config.py defaults: batch 256, hidden 256
+    (256, 256, "iso", 2, "geodesic", 0.2, 0.2, 15, 0.5),
+    (161, 256, "clustered", 3, "cosine", 0.07, 0.05, 15, 1.0),
+    (300, 64, "iso", 5, "geodesic", 0.1, 0.0, 32, 0.37),
+    (512, 256, "ties", 2, "cosine", 0.07, 0.0, 15, 0.5),
+    (512, 256, "iso", 2, "cosine", 0.07, 0.1, 600, 1.0),         # K >= all negatives
+    (400, 128, "iso", 7, "cosine", 0.5, 0.0, 0, 0.0),            # multi-class class: K = 0
+]
+
+
+@pytest.mark.parametrize("n,d,kind,classes,sim,tau,lam,k,alpha", MID_CASES)
+def test_mid_size_single_launch_kernel_fp32(cuda_device, n, d, kind, classes, sim, tau, lam, k, alpha):
+    """fp32, whole batch on one GPU, 160 < N <= 512: loss and dz from ONE cluster launch (default flags) agree with
+    the oracle at 1e-5 and with the tiled exact kernels (flags = 4) -- same formulas, same fixed k-order."""
+    x, y = O.make_inputs(n, d, kind, classes=classes)
+    z = F.normalize(x, dim=1)
+    kw = dict(tau=tau, similarity=sim, lam=lam, t=2.0, topk=k, alpha=alpha)
+    ref = G.oracle_for(z, y, **kw)
+    loss, dz = G.kernel_loss_and_grad(z, y, **kw)
+    assert loss == pytest.approx(ref["loss"], rel=TOL_F32, abs=1e-6)
+    assert G.rel_err(dz, ref["dz"]) < TOL_F32
+    loss_t, dz_t = G.kernel_loss_and_grad(z, y, flags=4, **kw)
+    assert loss_t == pytest.approx(loss, rel=1e-6)
+    assert G.rel_err(dz, dz_t) < 1e-5
+    if k >= 1 and alpha != 0.0:       # hard-negative thresholds: identical (value, index) in both kernel families
+        a = G.kernel_stats(z, y, flags=0, **{**kw, "alpha": alpha})
+        b = G.kernel_stats(z, y, flags=4, **{**kw, "alpha": alpha})
+        assert torch.equal(a["stats"].view(torch.int32)[:, _cabi.ST_THR_IDX], b["stats"].view(torch.int32)[:, _cabi.ST_THR_IDX])
+        assert torch.equal(a["stats"][:, _cabi.ST_THR_VAL], b["stats"][:, _cabi.ST_THR_VAL])

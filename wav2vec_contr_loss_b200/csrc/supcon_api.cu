@@ -80,6 +80,12 @@ bool use_small(const supcon_problem_t* p, const void* z) {
   if (p->flags & (SUPCON_FLAG_NO_SMALL | SUPCON_FLAG_FORCE_TENSOR)) return false;
   return small_supported(p, z);
 }
+// mid-size single-launch kernel: exact fp32 math, so it yields to the tensor path where that one is eligible
+bool use_mid(const supcon_problem_t* p, const void* z) {
+  if (p->flags & (SUPCON_FLAG_NO_SMALL | SUPCON_FLAG_FORCE_TENSOR)) return false;
+  if (use_tc(p, false) || use_tc(p, true)) return false;
+  return !small_supported(p, z) && mid_supported(p, z);
+}
 
 SmallArgs make_small(const supcon_problem_t* p, const void* z, const int32_t* labels) {
   SmallArgs s;
@@ -232,6 +238,14 @@ int supcon_forward_rows(const supcon_problem_t* p, const void* z_all, const int3
     if (es != cudaSuccess) return cuda_fail(es, "small_launch");
     return 0;
   }
+  if (use_mid(p, z_all)) {     // 160 < N <= 512: one cluster launch instead of the tiled kernels
+    SmallArgs s = make_small(p, z_all, labels_all);
+    s.row_stats = row_stats; s.partials = partials; s.loss_out = loss_out;
+    bool taken = false;
+    cudaError_t es = mid_launch(s, st, &taken);
+    if (es != cudaSuccess) return cuda_fail(es, "mid_launch");
+    if (taken) return 0;
+  }
   if (use_tc(p, false)) {
     const char* err = "";
     int rc = tc_forward(p, z_all, labels_all, row_stats, partials, loss_out, workspace, st, &err);
@@ -383,6 +397,14 @@ int supcon_loss_and_grad(const supcon_problem_t* p, const void* z, const int32_t
     cudaError_t es = small_launch(s, reinterpret_cast<cudaStream_t>(stream));
     if (es != cudaSuccess) return cuda_fail(es, "small_launch");
     return 0;
+  }
+  if (use_mid(p, z)) {     // forward AND backward of a mid-size batch in a single cluster launch
+    SmallArgs s = make_small(p, z, labels);
+    s.row_stats = row_stats; s.partials = partials; s.loss_out = loss_out; s.dz_out = dz_out; s.dz_dtype = dz_dtype;
+    bool taken = false;
+    cudaError_t es = mid_launch(s, reinterpret_cast<cudaStream_t>(stream), &taken);
+    if (es != cudaSuccess) return cuda_fail(es, "mid_launch");
+    if (taken) return 0;
   }
   int rc = supcon_forward_rows(p, z, labels, row_stats, partials, loss_out, workspace, workspace_bytes, stream);
   if (rc) return rc;

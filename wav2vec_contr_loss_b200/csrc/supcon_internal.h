@@ -145,6 +145,11 @@ struct SmallArgs {
 bool small_supported(const supcon_problem_t* p, const void* z);
 cudaError_t small_launch(const SmallArgs& a, cudaStream_t stream);
 
+// ---- single-launch mid-size path, 160 < N <= 512 (supcon_mid.cu); *taken = false when the device cannot
+//      co-schedule the cluster (the caller then uses the tiled kernels) ----
+bool mid_supported(const supcon_problem_t* p, const void* z);
+cudaError_t mid_launch(const SmallArgs& a, cudaStream_t stream, bool* taken);
+
 // ---- producer of z: compression head up to the Linear layer, fused with the time mean (supcon_head.cu) ----
 struct HeadPoolArgs {
   const float* hs;                      // [B][K][F][T]

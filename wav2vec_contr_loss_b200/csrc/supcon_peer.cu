@@ -16,6 +16,7 @@
 // before the consumers' loads.  Every spin is bounded (trap after ~seconds) so a protocol error cannot hang a GPU.
 // Kernels of DIFFERENT GPUs wait on one another; kernels of one GPU never do.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "supcon_common.cuh"
 #include "supcon_internal.h"
@@ -133,7 +134,12 @@ cudaError_t peer_push(const supcon_peer_t& pe, const void* src0, size_t bytes0, 
   // enough threads in flight to fill the NVLink egress (16 B per store), few enough to sit beside a compute kernel
   const size_t chunks = (bytes0 + a.bytes[1]) / 16 + 1;
   int blocks = (int)((chunks + 255) / 256);
-  if (blocks > 64) blocks = 64;
+  static const int max_blocks = [] {   // tuning knob, read once
+    const char* v = getenv("SUPCON_PEER_PUSH_BLOCKS");
+    const int n = (v && *v) ? atoi(v) : 64;
+    return n > 0 ? n : 64;
+  }();
+  if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   peer_push_kernel<<<blocks, 256, 0, stream>>>(a);
   return cudaGetLastError();

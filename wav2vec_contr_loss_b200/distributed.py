@@ -62,6 +62,8 @@ class _CudaKernels:
 
 
 _COMM_STREAMS = {}
+import os as _os
+_EXPERIMENT = _os.environ.get("SUPCON_PEER_EXPERIMENT", "")    # "noz", "nostats": skip an exchange (timing breakdown)
 
 
 def _comm_stream(device) -> "torch.cuda.Stream":
@@ -128,17 +130,21 @@ class PeerExchange:
         zb, yb = self.z_all[r * nl:(r + 1) * nl], self.labels_all[r * nl:(r + 1) * nl]
         zb.copy_(zc)                               # own block of the own buffer: only this rank's kernels read it
         yb.copy_(labels_local)
-        comm.wait_stream(cur)
-        with torch.cuda.stream(comm):              # rows + labels to every peer, beside the own-column forward
-            Fn.peer_push(self.desc, zb, self.off_z + r * nl * self.row_bytes, yb, self.off_labels + r * nl * 4,
-                         _cabi.PEER_FLAG_Z, wait_flag_id=_cabi.PEER_FLAG_DONE, include_self=False)
+        skip = _EXPERIMENT                         # timing experiments only (results are then stale): see tools/
+        if "noz" not in skip:
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):          # rows + labels to every peer, beside the own-column forward
+                Fn.peer_push(self.desc, zb, self.off_z + r * nl * self.row_bytes, yb, self.off_labels + r * nl * 4,
+                             _cabi.PEER_FLAG_Z, wait_flag_id=_cabi.PEER_FLAG_DONE, include_self=False)
         ws = kernels.forward_rows_local(self.z_all, self.labels_all, prob)
-        cur.wait_stream(comm)
-        Fn.peer_wait(self.desc, _cabi.PEER_FLAG_Z, dev)
+        if "noz" not in skip:
+            cur.wait_stream(comm)
+            Fn.peer_wait(self.desc, _cabi.PEER_FLAG_Z, dev)
         stats, partials = kernels.forward_rows_remote(self.z_all, self.labels_all, prob, ws)
-        Fn.peer_push(self.desc, stats, self.off_stats + r * nl * 4 * _cabi.STATS_STRIDE, partials,
-                     self.off_partials + r * 8 * _cabi.N_PARTIALS, _cabi.PEER_FLAG_STATS, include_self=True)
-        Fn.peer_wait(self.desc, _cabi.PEER_FLAG_STATS, dev)
+        if "nostats" not in skip:
+            Fn.peer_push(self.desc, stats, self.off_stats + r * nl * 4 * _cabi.STATS_STRIDE, partials,
+                         self.off_partials + r * 8 * _cabi.N_PARTIALS, _cabi.PEER_FLAG_STATS, include_self=True)
+            Fn.peer_wait(self.desc, _cabi.PEER_FLAG_STATS, dev)
         partials_global, loss = kernels.finalize_sets(prob, self.partial_sets)
         if want_grad:
             self.pending = True
