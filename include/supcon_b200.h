@@ -194,6 +194,8 @@ typedef struct supcon_peer {
                                  process (peer_bases[rank] = the own buffer)                                 */
   uint64_t off_flags;         /* byte offset of the flag block inside each buffer                           */
   int32_t* epoch;             /* DEVICE int, rank-local: number of the current step, initialised to 1       */
+  uint64_t mc_base;           /* multicast address of the buffers (NVSwitch writes one store into every rank's
+                                 buffer: multimem.st), or 0: one unicast store per peer                      */
 } supcon_peer_t;
 
 /* Copy up to two byte ranges (sizes multiples of 4; src1 may be NULL) to the same offsets of EVERY peer's buffer

@@ -45,7 +45,7 @@ class Problem(ctypes.Structure):
 class Peer(ctypes.Structure):
     """struct supcon_peer (include/supcon_b200.h)."""
     _fields_ = [("rank", c_int32), ("world", c_int32), ("peer_bases", c_void_p), ("off_flags", ctypes.c_uint64),
-                ("epoch", c_void_p)]
+                ("epoch", c_void_p), ("mc_base", ctypes.c_uint64)]
 
 
 PEER_FLAG_Z, PEER_FLAG_STATS, PEER_FLAG_DONE, PEER_NFLAGS = 0, 1, 2, 3

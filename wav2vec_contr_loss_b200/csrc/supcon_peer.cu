@@ -32,6 +32,12 @@ __device__ __forceinline__ int ld_flag(const int* p) {
 __device__ __forceinline__ void st_flag(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// one store that the NVSwitch replicates into EVERY rank's buffer (multicast mapping of the symmetric buffer)
+__device__ __forceinline__ void multimem_st16(unsigned long long mc_addr, const uint4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
 __device__ __forceinline__ int* flag_ptr(const supcon_peer_t& pe, int owner, int flag_id, int who) {
   return reinterpret_cast<int*>(pe.peer_bases[owner] + pe.off_flags) + flag_id * pe.world + who;
 }
@@ -52,7 +58,8 @@ struct PushArgs {
   int flag_id, wait_flag_id, include_self;
 };
 
-__global__ void __launch_bounds__(256) peer_push_kernel(PushArgs a) {
+// <= 40 registers (6 CTAs/SM bound): 256 x 40 regs fit beside the 320 x 168 of a forward CTA on the same SM
+__global__ void __launch_bounds__(256, 6) peer_push_kernel(PushArgs a) {
   const supcon_peer_t& pe = a.pe;
   const int e = *pe.epoch;
   // rank-local block counter behind the flags of the own buffer (zero between launches)
@@ -69,12 +76,38 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PushArgs a) {
     const char* src = a.src[sgm];
     const bool vec = ((reinterpret_cast<uintptr_t>(src) | a.dst_off[sgm]) & 15) == 0;
     const unsigned long long n16 = vec ? nb / 16 : 0;
-    for (long long i = tid; i < (long long)n16; i += nthr) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
-      for (int k = 1; k <= pe.world; ++k) {   // start with the next rank: spreads the traffic over the links
-        const int p = (pe.rank + k) % pe.world;
-        if (p == pe.rank && !a.include_self) continue;
-        reinterpret_cast<uint4*>(pe.peer_bases[p] + a.dst_off[sgm])[i] = v;
+    // Four independent 16-byte loads per thread before the stores: the copy is latency-bound (a load from HBM / L2
+    // and a posted store over NVLink each take ~1 us), so bytes in flight = bandwidth x latency must reach ~1 MB;
+    // one 16-byte load per thread in flight (first version) capped the push at ~300 GB/s.
+    constexpr int U = 4;
+    const uint4* s16 = reinterpret_cast<const uint4*>(src);
+    if (pe.mc_base != 0 && n16 > 0) {
+      // multicast: ONE store per 16 bytes leaves this GPU and the switch writes it into all world buffers (the own
+      // one included -- the same bytes the caller may already have put there).  Egress is bytes, not world x bytes.
+      const unsigned long long mc = pe.mc_base + a.dst_off[sgm];
+      for (long long i = tid; i < (long long)n16; i += U * nthr) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (i + u * nthr < (long long)n16) v[u] = __ldg(s16 + i + u * nthr);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (i + u * nthr < (long long)n16) multimem_st16(mc + 16ull * (unsigned long long)(i + u * nthr), v[u]);
+      }
+    } else {
+      for (long long i = tid; i < (long long)n16; i += U * nthr) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (i + u * nthr < (long long)n16) v[u] = __ldg(s16 + i + u * nthr);
+        for (int k = 1; k <= pe.world; ++k) {   // start with the next rank: spreads the traffic over the links
+          const int p = (pe.rank + k) % pe.world;
+          if (p == pe.rank && !a.include_self) continue;
+          uint4* dst = reinterpret_cast<uint4*>(pe.peer_bases[p] + a.dst_off[sgm]);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (i + u * nthr < (long long)n16) dst[i + u * nthr] = v[u];
+        }
       }
     }
     for (long long i = (long long)n16 * 4 + tid; i < (long long)(nb / 4); i += nthr) {   // 4-byte tail / unaligned
@@ -136,10 +169,18 @@ cudaError_t peer_push(const supcon_peer_t& pe, const void* src0, size_t bytes0, 
   int blocks = (int)((chunks + 255) / 256);
   static const int max_blocks = [] {   // tuning knob, read once
     const char* v = getenv("SUPCON_PEER_PUSH_BLOCKS");
-    const int n = (v && *v) ? atoi(v) : 64;
-    return n > 0 ? n : 64;
+    const int n = (v && *v) ? atoi(v) : 0;
+    return n > 0 ? n : 0;
   }();
-  if (blocks > max_blocks) blocks = max_blocks;
+  const int cap = max_blocks > 0 ? max_blocks : 64;
+  if (blocks > cap) blocks = cap;
+  // The push runs BESIDE the own-column forward, whose CTAs need the SM's maximum shared-memory carve-out.  CTAs
+  // of kernels that prefer different carve-outs cannot share an SM (the SM would have to drain to re-partition
+  // L1 / shared memory), so without this the 1-CTA-per-SM compute kernel waits for the push on every SM the push
+  // touches and nothing overlaps (measured: the whole push time was exposed).
+  static const cudaError_t carve = cudaFuncSetAttribute(peer_push_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                        (int)cudaSharedmemCarveoutMaxShared);
+  (void)carve;
   if (blocks < 1) blocks = 1;
   peer_push_kernel<<<blocks, 256, 0, stream>>>(a);
   return cudaGetLastError();

@@ -115,8 +115,17 @@ class PeerExchange:
             n, _cabi.STATS_STRIDE)
         self.partial_sets = b[self.off_partials:self.off_partials + self.world * 8 * _cabi.N_PARTIALS].view(
             torch.float64).view(self.world, _cabi.N_PARTIALS)
+        # NVSwitch multicast mapping of the same buffers, when the fabric offers one: a single store per 16 bytes
+        # reaches every rank (multimem.st), so a rank's egress is its block, not (world - 1) copies of it
+        mc = 0
+        if _os.environ.get("SUPCON_PEER_MULTICAST", "1") != "0":
+            try:
+                mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+            except Exception:  # noqa: BLE001
+                mc = 0
+        self.multicast = mc != 0
         self.desc = _cabi.Peer(rank=self.rank, world=self.world, peer_bases=self.peer_bases.data_ptr(),
-                               off_flags=self.off_flags, epoch=self.epoch.data_ptr())
+                               off_flags=self.off_flags, epoch=self.epoch.data_ptr(), mc_base=mc)
         self.pending = False                      # a forward whose backward has not run yet
 
     def forward(self, zc, labels_local, prob, kernels, want_grad: bool):
