@@ -30,6 +30,7 @@ EXPORTS = (
     "supcon_forward_rows_remote", "supcon_head_pool_forward", "supcon_head_pool_backward",
     "supcon_finalize_sets", "supcon_backward_rows_local", "supcon_backward_rows_remote",
     "supcon_peer_push", "supcon_peer_wait", "supcon_peer_end_step", "supcon_label_keys",
+    "supcon_peer_push_ordered", "supcon_peer_wait_mask", "supcon_forward_rows_pass",
 )
 
 
@@ -52,7 +53,7 @@ PEER_FLAG_Z, PEER_FLAG_STATS, PEER_FLAG_DONE, PEER_NFLAGS = 0, 1, 2, 3
 
 
 def peer_flag_bytes(world: int) -> int:
-    return (PEER_NFLAGS * world + 4) * 4
+    return (PEER_NFLAGS * world + 4 + world) * 4
 
 
 _lib = None
@@ -120,6 +121,14 @@ def load():
     lib.supcon_peer_push.restype = c_int32
     lib.supcon_peer_push.argtypes = [PP, c_void_p, c_size_t, ctypes.c_uint64, c_void_p, c_size_t, ctypes.c_uint64,
                                      c_int32, c_int32, c_int32, c_void_p]
+    lib.supcon_peer_push_ordered.restype = c_int32
+    lib.supcon_peer_push_ordered.argtypes = [PP, c_void_p, c_size_t, ctypes.c_uint64, c_void_p, c_size_t,
+                                             ctypes.c_uint64, c_int32, c_int32, c_void_p]
+    lib.supcon_peer_wait_mask.restype = c_int32
+    lib.supcon_peer_wait_mask.argtypes = [PP, c_int32, ctypes.c_uint64, c_void_p]
+    lib.supcon_forward_rows_pass.restype = c_int32
+    lib.supcon_forward_rows_pass.argtypes = [P, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.supcon_peer_wait.restype = c_int32
     lib.supcon_peer_wait.argtypes = [PP, c_int32, c_void_p]
     lib.supcon_peer_end_step.restype = c_int32

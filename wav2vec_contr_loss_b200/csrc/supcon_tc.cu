@@ -112,6 +112,12 @@ __device__ __forceinline__ float fixmax_from_bits(unsigned bits, float m_limit) 
   return m2 <= m_limit ? m2 : __int_as_float(0x7fc00000);   // beyond tau / 0.025: poison (NaN), see the header
 }
 
+// logical unit w of a launch that sweeps a list of equal-length blocks -> physical unit
+__host__ __device__ __forceinline__ int block_list_map(const TcBlockList& bl, int w) {
+  const int b = w / bl.len;
+  return bl.start[b] + (w - b * bl.len);
+}
+
 // padded labels + squared norms of `count` columns of [j_lo, n_pad) minus the window [ex_lo, ex_lo + ex_len),
 // and their running maximum (one atomic per block).  One warp per column, grid-stride.
 __global__ void __launch_bounds__(256) tc_prep_fwd_kernel(const __nv_bfloat16* __restrict__ z,
@@ -119,16 +125,18 @@ __global__ void __launch_bounds__(256) tc_prep_fwd_kernel(const __nv_bfloat16* _
                                                           int32_t* __restrict__ lab_pad, float* __restrict__ nrm_pad,
                                                           unsigned* __restrict__ nrm2_max, int count, int j_lo = 0,
                                                           int ex_lo = 0x7fffffff, int ex_len = 0,
-                                                          int track_max = 1) {
+                                                          int track_max = 1, TcBlockList bl = TcBlockList{0, 1, {0}},
+                                                          int read_z = 1) {
   __shared__ float wmax[8];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float mx = 0.f;
   for (int w = blockIdx.x * 8 + wib; w < count; w += gridDim.x * 8) {
     int j = j_lo + w;
     if (j >= ex_lo) j += ex_len;
+    if (bl.n > 0) j = block_list_map(bl, w);
     if (j >= n_pad) break;
     float s = 0.f;
-    if (j < n) {
+    if (j < n && read_z) {
       const __nv_bfloat16* zr = z + (int64_t)j * d;
       for (int k = 8 * lane; k < d; k += 256) {   // d % 8 == 0 on this path (d == 256): 16-byte loads
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(zr + k));
@@ -160,9 +168,14 @@ __global__ void __launch_bounds__(256) tc_prep_fwd_kernel(const __nv_bfloat16* _
 // class sizes: one thread per column of [j_lo, n) minus the excluded window; lanes holding the same label are
 // aggregated (__match_any_sync) so a binary batch costs two atomics per warp instead of 32 on two addresses
 __global__ void tc_label_table_kernel(const int32_t* __restrict__ labels, int n, unsigned long long* hkeys,
-                                      int* hcounts, uint32_t hmask, int j_lo, int ex_lo, int ex_len) {
+                                      int* hcounts, uint32_t hmask, int j_lo, int ex_lo, int ex_len,
+                                      TcBlockList bl = TcBlockList{0, 1, {0}}) {
   int j = j_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ex_lo) j += ex_len;
+  if (bl.n > 0) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    j = w < bl.n * bl.len ? block_list_map(bl, w) : n;
+  }
   const bool ok = j < n;
   const unsigned active = __ballot_sync(0xffffffffu, ok);
   if (!ok) return;
@@ -344,6 +357,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
 // logical column tile of this launch -> physical tile: a launch covers [ct_base, ...) minus an excluded window
 // (the two-phase multi-GPU forward first sweeps the rank's own columns, then everything else)
 __device__ __forceinline__ int fwd_col_tile(const TcFwdArgs& a, int ct) {
+  if (a.blocks.n > 0) return block_list_map(a.blocks, ct);
   return a.ct_base + ct + (ct >= a.ex_lo ? a.ex_len : 0);
 }
 
@@ -567,16 +581,18 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
     // partial records of this row: one per CTA whose unit range touches the row's 256-row block,
     // in CTA order = ascending column order
     const int rb = lr / (2 * TBM);
-    // slot list of this row: pass A (a.sched, slots from a.slot_base) and, in the two-phase forward, pass B
-    int slot_lo[2], slot_n[2];
-    slot_lo[0] = a.slot_base;
-    slot_n[0] = sched_cta_of(a.sched, (long long)rb * a.sched.T + a.sched.T - 1) -
-                sched_cta_of(a.sched, (long long)rb * a.sched.T) + 1;
-    slot_lo[1] = a.slot_base_b;
-    slot_n[1] = a.sched_b.P > 0 ? sched_cta_of(a.sched_b, (long long)rb * a.sched_b.T + a.sched_b.T - 1) -
-                                      sched_cta_of(a.sched_b, (long long)rb * a.sched_b.T) + 1
-                                : 0;
-    for (int ps = 0; ps < 2; ++ps)
+    // slot list of this row: one range of slots per pass of the forward (one, two or more passes)
+    int slot_lo[TC_MAX_PASSES], slot_n[TC_MAX_PASSES];
+    const int npass = a.npass;
+    for (int ps = 0; ps < TC_MAX_PASSES; ++ps) {
+      slot_lo[ps] = 0; slot_n[ps] = 0;
+      if (ps < npass) {
+        const TcSched& ms = a.msched[ps];
+        slot_lo[ps] = a.mslot[ps];
+        slot_n[ps] = sched_cta_of(ms, (long long)rb * ms.T + ms.T - 1) - sched_cta_of(ms, (long long)rb * ms.T) + 1;
+      }
+    }
+    for (int ps = 0; ps < npass; ++ps)
       for (int s = slot_lo[ps]; s < slot_lo[ps] + slot_n[ps]; ++s) {
         const float* rec = a.part + ((int64_t)s * a.rows_pad + lr) * 8;
         const float4 v = *reinterpret_cast<const float4*>(rec);
@@ -597,7 +613,7 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
       float* mv = mrg_v + threadIdx.x;   // entry e at mv[e * 128]
       int* mi = mrg_i + threadIdx.x;
       int cnt = 0;
-      for (int ps = 0; ps < 2; ++ps)
+      for (int ps = 0; ps < npass; ++ps)
         for (int s = slot_lo[ps]; s < slot_lo[ps] + slot_n[ps]; ++s) {
           const int64_t rec = (int64_t)s * a.rows_pad + lr;
           const int c = __float_as_int(a.part[rec * 8 + 5]);
@@ -1119,6 +1135,17 @@ TcPlan tc_plan(const supcon_problem_t* p) {
     pl.slots_local = sched_max_slots(pl.fwd_sched_local, pl.fwd_row_blocks);
     int both = pl.slots_local + sched_max_slots(pl.fwd_sched_remote, pl.fwd_row_blocks);
     if (both > pl.fwd_slots) pl.fwd_slots = both;
+    // multi-pass forward (tc_forward_pass): up to TC_MAX_PASSES passes over groups of rank blocks; a row block's
+    // records per pass never exceed those of the widest single-pass schedule seen over all group sizes
+    if (p->n_total % p->n_rows == 0) {
+      const int world = p->n_total / p->n_rows;
+      int worst = 1;
+      for (int k = 1; k <= world && k <= TC_MAX_BLOCKS; ++k) {
+        const int sl = sched_max_slots(make_sched(pl.fwd_row_blocks, k * pl.local_cts, sms, 0), pl.fwd_row_blocks);
+        if (sl > worst) worst = sl;
+      }
+      if (TC_MAX_PASSES * worst > pl.fwd_slots) pl.fwd_slots = TC_MAX_PASSES * worst;
+    }
     pl.bwd_sched_local = make_sched(pl.row_blocks, pl.bwd_local_cts, sms, 0, small_share ? kn.bwd_local_free_sms : 0);
     pl.bwd_sched_remote = make_sched(pl.row_blocks, pl.bwd_col_tiles - pl.bwd_local_cts, sms, kn.bwd_ctas);
     pl.bwd_slots_local = sched_max_slots(pl.bwd_sched_local, pl.row_blocks);
@@ -1209,6 +1236,43 @@ bool tc_bwd_two_phase(const supcon_problem_t* p) { return tc_two_phase(p) && !(p
 
 // phase: 0 = whole forward; 1 = only the columns this rank owns (partial records, needs nothing from other
 // ranks); 2 = all other columns + merge.  Phases 1 and 2 must use the same workspace.
+// common part of the forward launches: argument block that does not depend on the pass
+static TcFwdArgs fwd_base_args(const supcon_problem_t* p, const TcPlan& pl, char* ws) {
+  TcFwdArgs a;
+  a.hkeys = reinterpret_cast<const unsigned long long*>(ws + pl.off_hkeys);
+  a.hcounts = reinterpret_cast<const int*>(ws + pl.off_hcounts);
+  a.hmask = pl.hash_size - 1;
+  a.nrm2_max = reinterpret_cast<unsigned*>(ws) + WS_NRM2_MAX_WORD;
+  a.ct_base = 0; a.ex_lo = 0x7fffffff; a.ex_len = 0; a.slot_base = 0;
+  a.blocks.n = 0; a.blocks.len = 1;
+  a.npass = 0;
+  a.lab_pad = reinterpret_cast<const int32_t*>(ws + pl.off_lab);
+  a.nrm_pad = reinterpret_cast<const float*>(ws + pl.off_nrm);
+  a.part = reinterpret_cast<float*>(ws + pl.off_part);
+  a.n_total = p->n_total; a.n_pad = pl.n_pad; a.row_offset = p->row_offset; a.n_rows = p->n_rows;
+  a.rows_pad = pl.rows_pad; a.sched = pl.fwd_sched; a.topk = p->topk;
+  a.inv_tau = 1.0f / p->tau;
+  a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;   // c0: unit-row value; kernels derive theirs
+  a.m_limit = p->tau / 0.025f;
+  const bool mine = p->alpha != 0.f && p->topk >= 1;
+  a.mine = mine ? 1 : 0;
+  a.kcap = mine ? (p->topk < TC_KCAP ? p->topk : TC_KCAP) : 0;
+  a.topk_v = reinterpret_cast<float*>(ws + pl.off_topk_v);
+  a.topk_i = reinterpret_cast<int32_t*>(ws + pl.off_topk_i);
+  return a;
+}
+static cudaError_t fwd_launch_kernel(const supcon_problem_t* p, const CUtensorMap& tm, const void* z_all,
+                                     const TcFwdArgs& a, cudaStream_t stream) {
+  const size_t smem = 3 * (size_t)NBOX * 128 * 128 + 1024;   // 3 tile stages, or 2 stages + 64 KB of top-K lists
+  const int ctas = a.sched.P;
+  const bool geo = p->similarity == SUPCON_GEODESIC, uni = p->lambda_uni > 0.f, mine = a.mine != 0;
+  const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
+  if (geo && uni) return launch_fwd_m<SUPCON_GEODESIC, true>(mine, tm, zb, a, ctas, smem, stream);
+  if (geo) return launch_fwd_m<SUPCON_GEODESIC, false>(mine, tm, zb, a, ctas, smem, stream);
+  if (uni) return launch_fwd_m<SUPCON_COSINE, true>(mine, tm, zb, a, ctas, smem, stream);
+  return launch_fwd_m<SUPCON_COSINE, false>(mine, tm, zb, a, ctas, smem, stream);
+}
+
 int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, float* row_stats,
                double* partials, float* loss_out, void* workspace, cudaStream_t stream, const char** err, int phase) {
   const TcPlan pl = tc_plan(p);
@@ -1224,7 +1288,6 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
     if (e == cudaSuccess) e = cudaMemsetAsync(ws + pl.off_hkeys, 0, (size_t)pl.hash_size * 12, stream);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
   }
-  const bool uni = p->lambda_uni > 0.f;
   unsigned* nrm2_max = reinterpret_cast<unsigned*>(ws) + WS_NRM2_MAX_WORD;
   {
     // padded labels / squared norms (+ their maximum: the fixed maximum of the exponentials) of the columns
@@ -1251,45 +1314,103 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
           labels_all, p->n_total, reinterpret_cast<unsigned long long*>(ws + pl.off_hkeys),
           reinterpret_cast<int*>(ws + pl.off_hcounts), pl.hash_size - 1, jn_lo, jn_ex_lo, jn_ex_len);
   }
-  (void)uni;
-  TcFwdArgs a;
-  a.hkeys = reinterpret_cast<const unsigned long long*>(ws + pl.off_hkeys);
-  a.hcounts = reinterpret_cast<const int*>(ws + pl.off_hcounts);
-  a.hmask = pl.hash_size - 1;
-  a.nrm2_max = nrm2_max;
-  a.ct_base = 0; a.ex_lo = 0x7fffffff; a.ex_len = 0; a.slot_base = 0;
-  a.sched_b.P = 0; a.sched_b.T = 1; a.sched_b.U = 1; a.slot_base_b = 0;
-  a.lab_pad = reinterpret_cast<const int32_t*>(ws + pl.off_lab);
-  a.nrm_pad = reinterpret_cast<const float*>(ws + pl.off_nrm);
-  a.part = reinterpret_cast<float*>(ws + pl.off_part);
-  a.n_total = p->n_total; a.n_pad = pl.n_pad; a.row_offset = p->row_offset; a.n_rows = p->n_rows;
-  a.rows_pad = pl.rows_pad; a.sched = pl.fwd_sched; a.topk = p->topk;
+  TcFwdArgs a = fwd_base_args(p, pl, ws);
   if (phase == 1) { a.sched = pl.fwd_sched_local; a.ct_base = pl.local_ct0; }
   if (phase == 2) { a.sched = pl.fwd_sched_remote; a.ex_lo = pl.local_ct0; a.ex_len = pl.local_cts; a.slot_base = pl.slots_local; }
-  a.inv_tau = 1.0f / p->tau;
-  a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;   // c0: unit-row value; kernels derive theirs
-  a.m_limit = p->tau / 0.025f;
-  const bool mine = p->alpha != 0.f && p->topk >= 1;
-  a.mine = mine ? 1 : 0;
-  a.kcap = mine ? (p->topk < TC_KCAP ? p->topk : TC_KCAP) : 0;
-  a.topk_v = reinterpret_cast<float*>(ws + pl.off_topk_v);
-  a.topk_i = reinterpret_cast<int32_t*>(ws + pl.off_topk_i);
-  const size_t smem = 3 * (size_t)NBOX * 128 * 128 + 1024;   // 3 tile stages, or 2 stages + 64 KB of top-K lists
-  const int ctas = a.sched.P;
-  const bool geo = p->similarity == SUPCON_GEODESIC;
-  const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z_all);
-  if (geo && uni) e = launch_fwd_m<SUPCON_GEODESIC, true>(mine, tm, zb, a, ctas, smem, stream);
-  else if (geo) e = launch_fwd_m<SUPCON_GEODESIC, false>(mine, tm, zb, a, ctas, smem, stream);
-  else if (uni) e = launch_fwd_m<SUPCON_COSINE, true>(mine, tm, zb, a, ctas, smem, stream);
-  else e = launch_fwd_m<SUPCON_COSINE, false>(mine, tm, zb, a, ctas, smem, stream);
+  e = fwd_launch_kernel(p, tm, z_all, a, stream);
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
   if (phase == 1) return 0;   // partial records only; phase 2 merges
-  if (phase == 2) {           // merge sums the local-column records (pass A) and the remote ones (pass B)
-    a.sched_b = a.sched; a.slot_base_b = a.slot_base;
-    a.sched = pl.fwd_sched_local; a.slot_base = 0;
+  // the merge sums the records of every pass: one pass, or the own-column pass followed by the other columns
+  if (phase == 2) {
+    a.npass = 2;
+    a.msched[0] = pl.fwd_sched_local; a.mslot[0] = 0;
+    a.msched[1] = pl.fwd_sched_remote; a.mslot[1] = pl.slots_local;
+  } else {
+    a.npass = 1;
+    a.msched[0] = pl.fwd_sched; a.mslot[0] = 0;
   }
   FinishArgs f{reinterpret_cast<double*>(ws + pl.off_block_partials), reinterpret_cast<unsigned*>(ws), partials,
                loss_out, p->n_total, p->tau, p->alpha, p->lambda_uni, p->uni_t};
+  tc_fwd_merge_kernel<<<pl.merge_blocks, 128, 0, stream>>>(a, f, row_stats);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  return 0;
+}
+
+// Multi-pass forward for a rank of a row-sharded job whose peers' rows arrive over time: the columns are swept
+// rank block by rank block in the order given (own block first, then the peers in arrival order), grouped into
+// passes; each pass is one launch over all its blocks and needs only those blocks of z_all / labels_all.
+// blocks[] lists every pass's blocks back to back, pass_sizes[i] how many belong to pass i.
+int tc_forward_pass(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, const int32_t* blocks,
+                    const int32_t* pass_sizes, int n_passes, int pass_index, int skip_norms, float* row_stats,
+                    double* partials, void* workspace, cudaStream_t stream, const char** err) {
+  const TcPlan pl = tc_plan(p);
+  char* ws = reinterpret_cast<char*>(workspace);
+  if (!pl.two_phase || p->n_total % p->n_rows != 0) { *err = "multi-pass forward needs equal, 128-aligned row blocks"; return SUPCON_E_UNSUPPORTED; }
+  const int world = p->n_total / p->n_rows;
+  if (n_passes < 1 || n_passes > TC_MAX_PASSES || pass_index < 0 || pass_index >= n_passes) { *err = "bad pass index"; return SUPCON_E_INVALID; }
+  // schedules and first slots of every pass (the merge needs them all; each launch its own)
+  TcSched sched[TC_MAX_PASSES];
+  int slot0[TC_MAX_PASSES], first_block[TC_MAX_PASSES], total_blocks = 0, slots = 0;
+  const int sms = num_sms();
+  for (int i = 0; i < n_passes; ++i) {
+    if (pass_sizes[i] < 1 || pass_sizes[i] > TC_MAX_BLOCKS) { *err = "bad pass size"; return SUPCON_E_INVALID; }
+    first_block[i] = total_blocks;
+    total_blocks += pass_sizes[i];
+    sched[i] = make_sched(pl.fwd_row_blocks, pass_sizes[i] * pl.local_cts, sms, 0);
+    slot0[i] = slots;
+    slots += sched_max_slots(sched[i], pl.fwd_row_blocks);
+  }
+  if (total_blocks != world) { *err = "the passes must list every rank block exactly once"; return SUPCON_E_INVALID; }
+  if (slots > pl.fwd_slots) { *err = "multi-pass forward: more partial-record slots than the workspace holds"; return SUPCON_E_WORKSPACE; }
+  CUtensorMap tm;
+  if (int trc = make_bf16_rowmajor_tmap(&tm, z_all, (uint64_t)p->n_total, (uint64_t)p->d, 128)) {
+    *err = tmap_error(trc, z_all, p->n_total);
+    return SUPCON_E_INVALID;
+  }
+  cudaError_t e = cudaSuccess;
+  if (pass_index == 0) {
+    e = cudaMemsetAsync(workspace, 0, 256, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws + pl.off_hkeys, 0, (size_t)pl.hash_size * 12, stream);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  }
+  TcBlockList cols, tiles;   // this pass's blocks in column units and in 128-column tiles
+  cols.n = tiles.n = pass_sizes[pass_index];
+  cols.len = p->n_rows; tiles.len = pl.local_cts;
+  for (int b = 0; b < cols.n; ++b) {
+    const int blk = blocks[first_block[pass_index] + b];
+    if (blk < 0 || blk >= world) { *err = "bad block index"; return SUPCON_E_INVALID; }
+    cols.start[b] = blk * p->n_rows;
+    tiles.start[b] = blk * pl.local_cts;
+  }
+  const int count = cols.n * cols.len;
+  {
+    int nb = (count + 7) / 8;
+    const int cap = 8 * sms;
+    if (nb > cap) nb = cap;
+    // skip_norms: labels only (rows of z not read): the caller vouches for unit rows of the peers' blocks, which
+    // each rank checks for its own rows (pass 0 always reads its rows)
+    const int read_z = (skip_norms && pass_index > 0 && !(p->lambda_uni > 0.f)) ? 0 : 1;
+    tc_prep_fwd_kernel<<<nb, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all, p->n_total,
+                                               pl.n_pad, p->d, reinterpret_cast<int32_t*>(ws + pl.off_lab),
+                                               reinterpret_cast<float*>(ws + pl.off_nrm),
+                                               reinterpret_cast<unsigned*>(ws) + WS_NRM2_MAX_WORD, count, 0, 0x7fffffff, 0,
+                                               (p->similarity == SUPCON_COSINE && read_z) ? 1 : 0, cols, read_z);
+    tc_label_table_kernel<<<(count + 255) / 256, 256, 0, stream>>>(
+        labels_all, p->n_total, reinterpret_cast<unsigned long long*>(ws + pl.off_hkeys),
+        reinterpret_cast<int*>(ws + pl.off_hcounts), pl.hash_size - 1, 0, 0x7fffffff, 0, cols);
+  }
+  TcFwdArgs a = fwd_base_args(p, pl, ws);
+  a.sched = sched[pass_index];
+  a.slot_base = slot0[pass_index];
+  a.blocks = tiles;
+  e = fwd_launch_kernel(p, tm, z_all, a, stream);
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+  if (pass_index + 1 < n_passes) return 0;
+  a.npass = n_passes;
+  for (int i = 0; i < n_passes; ++i) { a.msched[i] = sched[i]; a.mslot[i] = slot0[i]; }
+  FinishArgs f{reinterpret_cast<double*>(ws + pl.off_block_partials), reinterpret_cast<unsigned*>(ws), partials,
+               nullptr, p->n_total, p->tau, p->alpha, p->lambda_uni, p->uni_t};
   tc_fwd_merge_kernel<<<pl.merge_blocks, 128, 0, stream>>>(a, f, row_stats);
   e = cudaGetLastError();
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }

@@ -55,6 +55,7 @@ class _CudaKernels:
     # two-phase forward: own columns while the all-gather is in flight, then the rest
     forward_rows_local = staticmethod(Fn.forward_rows_local)
     forward_rows_remote = staticmethod(Fn.forward_rows_remote)
+    forward_rows_pass = staticmethod(Fn.forward_rows_pass)
     # two-phase backward: own columns while the statistics are exchanged, then the rest
     backward_rows_local = staticmethod(Fn.backward_rows_local)
     backward_rows_remote = staticmethod(Fn.backward_rows_remote)
@@ -127,6 +128,46 @@ class PeerExchange:
         self.desc = _cabi.Peer(rank=self.rank, world=self.world, peer_bases=self.peer_bases.data_ptr(),
                                off_flags=self.off_flags, epoch=self.epoch.data_ptr(), mc_base=mc)
         self.pending = False                      # a forward whose backward has not run yet
+        # Arrival order of the peers' blocks under the ordered push (everybody sends to rank+1 first): rank-1, rank-2,
+        # ...  The forward sweeps the own block, then the first ~3/7 of the peers, then the rest: while it works on a
+        # group the next one is still landing.
+        order = [(self.rank - k) % self.world for k in range(1, self.world)]
+        n_first = max(1, round(len(order) * 3 / 7)) if len(order) >= 3 else len(order)
+        groups = [order[:n_first], order[n_first:]] if len(order) > n_first else [order]
+        self.groups = [g_ for g_ in groups if g_]
+        self.passes = Fn.ForwardPasses([[self.rank]] + self.groups)
+        self.masks = [sum(1 << p_ for p_ in g_) for g_ in self.groups]
+
+    def pipelined_ok(self, prob, kernels) -> bool:
+        """Ordered push + multi-pass forward: tensor path, aligned equal blocks, no uniformity term (its norms and
+        coefficient need every row before the sweep), at least three ranks."""
+        from . import _cabi
+        return (self.world >= 3 and hasattr(kernels, "forward_rows_pass") and prob.z_dtype == _cabi.BF16
+                and prob.d == 256 and self.n_local % 128 == 0 and prob.lambda_uni == 0.0 and prob.tau >= 0.025
+                and (prob.similarity == _cabi.GEODESIC or (prob.flags & (_cabi.FLAG_UNIT_ROWS | _cabi.FLAG_FORCE_TENSOR)))
+                and not (prob.flags & _cabi.FLAG_FORCE_EXACT) and (prob.alpha == 0.0 or prob.topk <= 32)
+                and "nopipe" not in _EXPERIMENT)
+
+    def forward_pipelined(self, zc, labels_local, prob, kernels, want_grad: bool):
+        """rows to the peers in ring order | own columns -> first arrivals -> later arrivals -> statistics out."""
+        from . import _cabi
+        r, nl, dev = self.rank, self.n_local, self.device
+        cur, comm = torch.cuda.current_stream(dev), _comm_stream(dev)
+        zb, yb = self.z_all[r * nl:(r + 1) * nl], self.labels_all[r * nl:(r + 1) * nl]
+        zb.copy_(zc)
+        yb.copy_(labels_local)
+        comm.wait_stream(cur)
+        with torch.cuda.stream(comm):
+            Fn.peer_push_ordered(self.desc, zb, self.off_z + r * nl * self.row_bytes, yb, self.off_labels + r * nl * 4,
+                                 _cabi.PEER_FLAG_Z, wait_flag_id=_cabi.PEER_FLAG_DONE)
+        ws = kernels.forward_rows_pass(self.z_all, self.labels_all, prob, self.passes, 0)
+        out = None
+        for i, mask in enumerate(self.masks):
+            Fn.peer_wait(self.desc, _cabi.PEER_FLAG_Z, dev, rank_mask=mask)
+            out = kernels.forward_rows_pass(self.z_all, self.labels_all, prob, self.passes, i + 1, ws)
+        stats, partials = out
+        cur.wait_stream(comm)                      # the own push has long finished; joins the side stream
+        return stats, partials
 
     def forward(self, zc, labels_local, prob, kernels, want_grad: bool):
         """push rows | own-column forward -> wait -> other columns -> push statistics -> wait -> loss."""
@@ -135,11 +176,14 @@ class PeerExchange:
             raise RuntimeError("ShardedSupConLoss (peer exchange): forward() called again before the backward of the "
                                "previous call; the exchange buffers hold what that backward reads")
         r, nl, dev = self.rank, self.n_local, self.device
+        skip = _EXPERIMENT                         # timing experiments only (results are then stale): see tools/
+        if self.pipelined_ok(prob, kernels) and "noz" not in skip:
+            stats, partials = self.forward_pipelined(zc, labels_local, prob, kernels, want_grad)
+            return self._finish_forward(stats, partials, prob, kernels, want_grad, skip)
         cur, comm = torch.cuda.current_stream(dev), _comm_stream(dev)
         zb, yb = self.z_all[r * nl:(r + 1) * nl], self.labels_all[r * nl:(r + 1) * nl]
         zb.copy_(zc)                               # own block of the own buffer: only this rank's kernels read it
         yb.copy_(labels_local)
-        skip = _EXPERIMENT                         # timing experiments only (results are then stale): see tools/
         if "noz" not in skip:
             comm.wait_stream(cur)
             with torch.cuda.stream(comm):          # rows + labels to every peer, beside the own-column forward
@@ -150,6 +194,12 @@ class PeerExchange:
             cur.wait_stream(comm)
             Fn.peer_wait(self.desc, _cabi.PEER_FLAG_Z, dev)
         stats, partials = kernels.forward_rows_remote(self.z_all, self.labels_all, prob, ws)
+        return self._finish_forward(stats, partials, prob, kernels, want_grad, skip)
+
+    def _finish_forward(self, stats, partials, prob, kernels, want_grad, skip):
+        """statistics + partial sums to every rank, wait for everybody's, loss."""
+        from . import _cabi
+        r, nl, dev = self.rank, self.n_local, self.device
         if "nostats" not in skip:
             Fn.peer_push(self.desc, stats, self.off_stats + r * nl * 4 * _cabi.STATS_STRIDE, partials,
                          self.off_partials + r * 8 * _cabi.N_PARTIALS, _cabi.PEER_FLAG_STATS, include_self=True)
