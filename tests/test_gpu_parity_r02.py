@@ -316,7 +316,7 @@ def test_duplicate_rows_with_uniformity(cuda_device, family, sim):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# single-launch kernel for mid-size batches, 160 < N <= 384 (supcon_mid.cu): the reference's default batch (256)
+# single-launch kernel for mid-size batches, 160 < N <= 320 (supcon_mid.cu): the reference's default batch (256)
 # ---------------------------------------------------------------------------------------------------------
 MID_CASES = [
     # n, d, kind, classes, sim, tau, lam, K, alpha
@@ -324,15 +324,15 @@ MID_CASES = [
     (256, 256, "iso", 2, "geodesic", 0.2, 0.2, 15, 0.5),
     (161, 256, "clustered", 3, "cosine", 0.07, 0.05, 15, 1.0),
     (300, 64, "iso", 5, "geodesic", 0.1, 0.0, 32, 0.37),
-    (384, 256, "ties", 2, "cosine", 0.07, 0.0, 15, 0.5),
-    (384, 256, "iso", 2, "cosine", 0.07, 0.1, 600, 1.0),         # K >= all negatives
-    (352, 128, "iso", 7, "cosine", 0.5, 0.0, 0, 0.0),            # multi-class class: K = 0
+    (320, 256, "ties", 2, "cosine", 0.07, 0.0, 15, 0.5),
+    (320, 256, "iso", 2, "cosine", 0.07, 0.1, 600, 1.0),         # K >= all negatives
+    (288, 128, "iso", 7, "cosine", 0.5, 0.0, 0, 0.0),            # multi-class class: K = 0
 ]
 
 
 @pytest.mark.parametrize("n,d,kind,classes,sim,tau,lam,k,alpha", MID_CASES)
 def test_mid_size_single_launch_kernel_fp32(cuda_device, n, d, kind, classes, sim, tau, lam, k, alpha):
-    """fp32, whole batch on one GPU, 160 < N <= 384: loss and dz from ONE cluster launch (default flags) agree with
+    """fp32, whole batch on one GPU, 160 < N <= 320: loss and dz from ONE cluster launch (default flags) agree with
     the oracle at 1e-5 and with the tiled exact kernels (flags = 4) -- same formulas, same fixed k-order."""
     x, y = O.make_inputs(n, d, kind, classes=classes)
     z = F.normalize(x, dim=1)

@@ -1,4 +1,4 @@
-// Single-launch SupCon forward + backward for MID-SIZE batches, 160 < N <= 384 -- the reference's own default
+// Single-launch SupCon forward + backward for MID-SIZE batches, 160 < N <= 320 -- the reference's own default
 // batch (stage1_config.py:22 BATCH_SIZE = 256) in its own dtype (fp32).  Same plan as supcon_small.cu (one
 // thread-block cluster, exact fp32 FFMA dot products in one fixed k-order, warp-per-row statistics, row
 // statistics exchanged through distributed shared memory between two cluster barriers, then H rows and dz rows)
@@ -6,8 +6,8 @@
 //   * only the CTA's OWN rows of z are staged in shared memory; the columns stream from global memory (z is
 //     <= 512 KB and L2-resident: every CTA reads it twice), so shared memory no longer has to hold all of z;
 //   * the cluster has 16 CTAs (non-portable size; 8 when the device cannot co-schedule 16), up to 32 rows each.
-// At these sizes the tiled exact path needs 5 launches and ~180 us (N = 256); this kernel is one launch
-// (measured N = 256: 107 us before the loads were software-pipelined; profiles/r02_small_batch_times.md).
+// At these sizes the tiled exact path needs 5 launches and ~180 us (N = 256); this kernel is one launch and takes
+// 107 us (N = 256, profiles/r02_small_batch_times.md).  Keeping two loads in flight by hand made it slower (125 us).
 //
 // c_ij is accumulated as ONE fma chain over k = 0..d-1, so c_ij == c_ji bit for bit and the backward's
 // hard-negative membership test (threshold value + index) sees exactly the forward's values.
@@ -23,7 +23,7 @@ namespace {
 
 constexpr int MNT = 256;     // threads per CTA
 constexpr int MMAXR = 32;    // owned rows per CTA
-constexpr int MMAXN = 384;   // columns (measured: beyond ~400 rows the tiled kernels' many CTAs win again)
+constexpr int MMAXN = 320;   // columns (measured: from ~384 rows on the tiled kernels' many CTAs are as fast)
 constexpr int MCOLS = MMAXN / 32;   // columns per lane in the statistics phase
 
 struct MidLayout {
@@ -91,13 +91,8 @@ __global__ void __launch_bounds__(MNT, 1) mid_kernel(SmallArgs a) {
     for (int r = 0; r < MMAXR; ++r) acc[r] = 0.f;
     float nj = 0.f;
     if (j < n) {
-      // the column's values come from L2 (~600 cycles): keep the next two float4 in flight while this one is used
-      float4 b0 = ld_row4<T>(z, j, true, 0, d, true);
-      float4 b1 = ld_row4<T>(z, j, d > 4, 4, d, true);
       for (int k = 0; k < d; k += 4) {
-        const float4 b = b0;
-        b0 = b1;
-        b1 = ld_row4<T>(z, j, k + 8 < d, k + 8, d, true);
+        const float4 b = ld_row4<T>(z, j, true, k, d, true);
         nj = fmaf(b.x, b.x, nj); nj = fmaf(b.y, b.y, nj); nj = fmaf(b.z, b.z, nj); nj = fmaf(b.w, b.w, nj);
 #pragma unroll
         for (int r = 0; r < MMAXR; ++r) {
@@ -298,16 +293,10 @@ __global__ void __launch_bounds__(MNT, 1) mid_kernel(SmallArgs a) {
     float acc[MMAXR];
 #pragma unroll
     for (int r = 0; r < MMAXR; ++r) acc[r] = 0.f;
-    float zn[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) zn[u] = (u < n) ? ld_elem<T>(z + (int64_t)u * d + dd) : 0.f;
     for (int j = 0; j < L.np; j += 4) {
       float zv[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {      // next four rows of z in flight while these are used
-        zv[u] = zn[u];
-        zn[u] = (j + 4 + u < n) ? ld_elem<T>(z + (int64_t)(j + 4 + u) * d + dd) : 0.f;
-      }
+      for (int u = 0; u < 4; ++u) zv[u] = (j + u < n) ? ld_elem<T>(z + (int64_t)(j + u) * d + dd) : 0.f;
 #pragma unroll
       for (int r = 0; r < MMAXR; ++r) {
         if (r < nrows) {

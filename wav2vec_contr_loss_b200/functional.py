@@ -183,7 +183,7 @@ def loss_and_grad(z: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Problem
     return loss, dz, stats, partials
 
 
-SMALL_BATCH_MAX = 384   # supcon_small.cu (N <= 160) and supcon_mid.cu (N <= 384): forward + backward in one launch
+SMALL_BATCH_MAX = 320   # supcon_small.cu (N <= 160) and supcon_mid.cu (N <= 320): forward + backward in one launch
 
 
 def forward_rows_local(z_all, labels_i32, prob: _cabi.Problem) -> torch.Tensor:
