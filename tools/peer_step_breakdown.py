@@ -3,8 +3,8 @@
 Captures the step (ShardedSupConLoss + autograd, exactly bench.py's) as a CUDA graph under several settings and
 times 20 replays each (CUDA events, L2 flushed, max over ranks):
   full           the real step
-  nopipe         rows pushed to all peers at once, forward in two phases (own columns, then all others after one wait)
-                 instead of the ordered push + multi-pass forward
+  pipe           ordered push (rank+1 first, ...) + multi-pass forward (own block, first arrivals, later arrivals)
+                 instead of one push to all peers and a two-phase forward
   noz            rows are NOT pushed / waited for (stale z: timing only)  -> full - noz  = exposed z exchange
   nostats        statistics are NOT pushed / waited for                   -> full - this = exposed stats exchange
   noz,nostats    neither                                                  -> kernels + launch structure only
@@ -31,7 +31,7 @@ out = {"world": world, "N": n}
 keep = []      # modules, graphs and outputs stay alive: freeing symmetric memory during a later capture is an error
 rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 2     # the whole list is measured `rounds` times: order effects show
 for rnd, exchange in [(r_, e_) for r_ in range(rounds) for e_ in ("peer", "nccl")]:
-    for variant in (("", "nopipe", "nostats", "noz,nostats") if exchange == "peer" else ("",)):
+    for variant in (("", "pipe", "noz", "nostats", "noz,nostats") if exchange == "peer" else ("",)):
         D._EXPERIMENT = variant
         mod = D.ShardedSupConLoss(0.07, "cosine", exchange=exchange)
         mod.assume_unit_rows = True

@@ -41,8 +41,8 @@ def _digest():
     files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + \
         [os.path.join(REPO_ROOT, "include", "supcon_b200.h"), os.path.abspath(__file__)]
     for f in files:
-        with open(f, "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
+        with open(f, "rb") as fh:     # keyed by the path RELATIVE to the repo: the tree is copied to other roots (gpurun)
+            h.update(os.path.relpath(f, REPO_ROOT).encode() + b"\0" + fh.read())
     return h.hexdigest()
 
 
@@ -54,8 +54,19 @@ def nvcc_path():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile (if stale) and return the path of the shared library."""
+    """Compile (if stale) and return the path of the shared library.  Safe to call from several processes at
+    once (one rank per GPU): the build runs under an exclusive file lock and the others find it done."""
+    import fcntl
     os.makedirs(LIB_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     digest = _digest()
     if not force and os.path.isfile(LIB_PATH) and os.path.isfile(TEST_LIB_PATH) and os.path.isfile(STAMP):
         with open(STAMP) as fh:

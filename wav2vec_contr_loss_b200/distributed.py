@@ -140,13 +140,16 @@ class PeerExchange:
 
     def pipelined_ok(self, prob, kernels) -> bool:
         """Ordered push + multi-pass forward: tensor path, aligned equal blocks, no uniformity term (its norms and
-        coefficient need every row before the sweep), at least three ranks."""
+        coefficient need every row before the sweep), at least three ranks.  OFF unless SUPCON_PEER_EXPERIMENT=pipe:
+        measured on 8 B200s it is SLOWER than pushing to all peers at once (0.83-0.85 ms vs 0.78 ms per step,
+        profiles/r02_peer_exchange_breakdown.md): three forward launches and a push serialised by destination cost more
+        than the earlier start buys."""
         from . import _cabi
         return (self.world >= 3 and hasattr(kernels, "forward_rows_pass") and prob.z_dtype == _cabi.BF16
                 and prob.d == 256 and self.n_local % 128 == 0 and prob.lambda_uni == 0.0 and prob.tau >= 0.025
                 and (prob.similarity == _cabi.GEODESIC or (prob.flags & (_cabi.FLAG_UNIT_ROWS | _cabi.FLAG_FORCE_TENSOR)))
                 and not (prob.flags & _cabi.FLAG_FORCE_EXACT) and (prob.alpha == 0.0 or prob.topk <= 32)
-                and "nopipe" not in _EXPERIMENT)
+                and "pipe" in _EXPERIMENT.split(","))
 
     def forward_pipelined(self, zc, labels_local, prob, kernels, want_grad: bool):
         """rows to the peers in ring order | own columns -> first arrivals -> later arrivals -> statistics out."""
