@@ -381,3 +381,41 @@ def test_multi_pass_forward_equals_single_sweep(cuda_device, sim, alpha, k):
             assert torch.allclose(s1[:, [0, 1, 6, 7]], s2[:, [0, 1, 6, 7]], rtol=1e-5, atol=1e-6)
             assert torch.allclose(p1[:5], p2[:5], rtol=1e-6)
             assert torch.equal(p1[5:], p2[5:])                                           # global counts, fixed maximum
+
+
+# ---------------------------------------------------------------------------------------------------------
+# backward beyond L2: the work list ordered by column panels (z > 48 MB)
+# ---------------------------------------------------------------------------------------------------------
+def test_backward_column_panels_beyond_l2(cuda_device):
+    """N = 131072 (z = 64 MB -> the backward's list is cut into 3 column panels): dz of a rank's 8192 rows, sampled
+    windows against the oracle's brute force (which is given every row's statistics from the forward, themselves
+    checked on the sampled rows), and the whole block against a second evaluation that shifts the panel boundaries
+    (another row offset -> other CTA ranges): the partial records of the panels must add up identically."""
+    n, nl, tau = 131072, 8192, 0.07
+    x, y = O.make_inputs(n, 256, "iso")
+    zb = F.normalize(x, dim=1).to(torch.bfloat16)
+    zz = Fn.canonical_z(zb.to(cuda_device))
+    yy = Fn.canonical_labels(y.to(cuda_device), n)
+    whole = _tc_problem(n, tau=tau, topk=15, alpha=0.0)
+    stats_all, partials, loss = Fn.forward_rows(zz, yy, whole, want_loss=True)
+    assert float(loss) == pytest.approx(math.log(n - 1) + 0.5 / (256 * tau * tau), rel=2e-3)
+    r0 = 5 * nl
+    prob = _tc_problem(n, tau=tau, topk=15, alpha=0.0, row_offset=r0, n_rows=nl)
+    dz = Fn.backward_rows(zz, yy, stats_all, partials, None, prob, out_dtype=torch.float32)
+    st = stats_all.cpu()
+    stats_dict = dict(lse=st[:, _cabi.ST_LSE].double(), lse_m=st[:, _cabi.ST_LSE].double(),
+                      npos=st.view(torch.int32)[:, _cabi.ST_NPOS].long(), nneg=st.view(torch.int32)[:, _cabi.ST_NNEG].long(),
+                      thr_val=torch.full((n,), float("inf"), dtype=torch.float64),
+                      thr_idx=torch.full((n,), -1, dtype=torch.int64), wsum=torch.zeros(n, dtype=torch.float64),
+                      pos_mean=st[:, _cabi.ST_POS_MEAN].double())
+    _, coef = O.loss_from_partials(partials.cpu(), n, alpha=0.0, lambda_uni=0.0)
+    z64 = zb.double()
+    for w0 in (r0, r0 + 4093, r0 + nl - 16):
+        fw, _ = O.rowblock_forward(z64, y, w0, 16, tau=tau, similarity=O.COSINE, topk=15)
+        assert float((st[w0:w0 + 16, _cabi.ST_LSE].double() - fw["lse"]).abs().max()) < 1e-4
+        want = O.rowblock_backward(z64, y, w0, 16, stats_dict, coef, tau=tau, similarity=O.COSINE, topk=15)
+        assert G.rel_err(dz[w0 - r0:w0 - r0 + 16].cpu(), want) < TOL_BF16, f"rows {w0}.."
+    # the same rows as part of a differently placed block: other CTA ranges / panel cuts, same sums
+    prob2 = _tc_problem(n, tau=tau, topk=15, alpha=0.0, row_offset=r0 - 2048, n_rows=nl)
+    dz2 = Fn.backward_rows(zz, yy, stats_all, partials, None, prob2, out_dtype=torch.float32)
+    assert G.rel_err(dz2[2048:].cpu(), dz[:nl - 2048].cpu()) < 1e-5

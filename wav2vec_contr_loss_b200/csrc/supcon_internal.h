@@ -48,6 +48,12 @@ struct TcSched {   // flattened (row block, column tile) work list cut into P co
   int T;           // column tiles per row block
   int P;           // CTAs
   long long U;     // row_blocks * T
+  // Column PANELS (backward at large N): the list is ordered (panel, row block, tile within the panel) instead of
+  // (row block, tile), so that the CTAs running at the same time work on a few panels of z instead of all of it and
+  // the Z_J tiles they stream stay in L2.  NP == 1: one panel = the plain row-major order.
+  int RB;          // row blocks
+  int NP;          // panels
+  int Tp;          // tiles per panel (the last panel holds the remainder)
 };
 struct TcPlan {
   TcSched fwd_sched, bwd_sched;
@@ -57,6 +63,7 @@ struct TcPlan {
   int local_ct0, local_cts, slots_local;       // forward: own-column window in 128-column tiles
   int bwd_local_ct0, bwd_local_cts, bwd_slots_local;   // backward: the same window in 64-column tiles
   int n_pad, rows_pad, row_blocks, fwd_row_blocks, fwd_col_tiles, bwd_col_tiles, fwd_slots, bwd_slots, merge_blocks;
+  int bwd_spp;                                 // backward: partial-record slots per column panel
   size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
       off_scalars, off_hkeys, off_hcounts, off_topk_v, off_topk_i, off_part, total_bytes;
   uint32_t hash_size;
@@ -112,6 +119,7 @@ struct TcBwdArgs {
   TcSched sched;
   TcSched sched_b;       // reduce only: second pass of the two-phase backward (P == 0: none)
   int ct_base, ex_lo, ex_len, slot_base, slot_base_b;
+  int spp;               // partial-record slots per panel of `sched`
   int n_total, n_pad, row_offset, n_rows, rows_pad;
   float c1, c0, ut2;
 };

@@ -238,6 +238,30 @@ __host__ __device__ inline int sched_cta_of(const TcSched& s, long long u) {
   return c;
 }
 
+// unit u of a (possibly panel-ordered) list -> row block, first column tile, tiles left in this row block's run
+struct SchedRun { int rb, ct0, run, panel; };
+__host__ __device__ inline int sched_panel_tiles(const TcSched& s, int panel) {
+  return (panel == s.NP - 1) ? s.T - (s.NP - 1) * s.Tp : s.Tp;
+}
+__host__ __device__ inline long long sched_first_unit(const TcSched& s, int panel, int rb) {
+  return (long long)panel * s.RB * s.Tp + (long long)rb * sched_panel_tiles(s, panel);
+}
+__host__ __device__ inline SchedRun sched_decode(const TcSched& s, long long u) {
+  SchedRun r;
+  if (s.NP <= 1) {
+    r.panel = 0; r.rb = (int)(u / s.T); r.ct0 = (int)(u % s.T); r.run = s.T - r.ct0;
+    return r;
+  }
+  const long long per = (long long)s.RB * s.Tp;
+  int p = (int)(u / per);
+  if (p > s.NP - 1) p = s.NP - 1;
+  const long long w = u - p * per;
+  const int tp = sched_panel_tiles(s, p);
+  const int o = (int)(w % tp);
+  r.panel = p; r.rb = (int)(w / tp); r.ct0 = p * s.Tp + o; r.run = tp - o;
+  return r;
+}
+
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
@@ -811,8 +835,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
     // ===== TMA producer (lane 0) + column-vector staging (all lanes) =====
     int g = 0;
     for (long long u = u_begin; u < u_end;) {
-      const int ct0 = (int)(u % sc.T);
-      const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
+      const SchedRun sr = sched_decode(sc, u);
+      const int ct0 = sr.ct0;
+      const int nt = (int)min((long long)sr.run, u_end - u);
       for (int t = 0; t < nt; ++t, ++g) {
         const int st = g % STAGES, use = g / STAGES, slot = g % RING;
         const int col0 = bwd_col_tile(a, ct0 + t) * BN;
@@ -860,8 +885,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       constexpr uint32_t idesc_dz = ptx::idesc_bf16(128, TD, false, true);
       int g0 = 0, seg = 0;
       for (long long u = u_begin; u < u_end; ++seg) {
-        const int ct0 = (int)(u % sc.T);
-        const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
+        const int nt = (int)min((long long)sched_decode(sc, u).run, u_end - u);
         ptx::mbar_wait(&bar_a, seg & 1);              // Z_I of this segment is in tensor memory
         ptx::mbar_wait(&bar_dzfree, (seg & 1) ^ 1);   // previous segment's dZ has been read out
         for (int t = 0; t <= nt; ++t) {
@@ -908,8 +932,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
     const uint32_t sbuf = tmem + lane_addr + TM_S + wg * BN;
     int g0 = 0, seg = 0;
     for (long long u = u_begin; u < u_end; ++seg) {
-      const int rb = (int)(u / sc.T), ct0 = (int)(u % sc.T);
-      const int nt = (int)min((long long)(sc.T - ct0), u_end - u);
+      const SchedRun sr = sched_decode(sc, u);
+      const int rb = sr.rb, ct0 = sr.ct0;
+      const int nt = (int)min((long long)sr.run, u_end - u);
       const int row0 = a.row_offset + rb * TBM;
       const int gi = row0 + lrow;
       if (wg == 0) {
@@ -960,7 +985,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       ptx::mbar_wait(&bar_done, seg & 1);
       ptx::tc_fence_after_sync();
       const bool row_ok = gi < a.row_offset + a.n_rows;
-      const int slot_out = a.slot_base + (int)blockIdx.x - sched_cta_of(sc, (long long)rb * sc.T);
+      // one partial record per (panel, CTA touching this row block within the panel)
+      const int slot_out = a.slot_base + sr.panel * a.spp + (int)blockIdx.x -
+                           sched_cta_of(sc, sched_first_unit(sc, sr.panel, rb));
       float* outp = a.dz_part + ((int64_t)slot_out * a.rows_pad + (gi - a.row_offset)) * TD + 128 * wg;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -997,20 +1024,21 @@ __global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const _
   if (lr >= a.n_rows) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int rb = lr / TBM;
-  // pass A (a.sched, slots from a.slot_base) and, after a two-phase backward, pass B
-  int slot_lo[2], slot_n[2];
-  slot_lo[0] = a.slot_base;
-  slot_n[0] = sched_cta_of(a.sched, (long long)rb * a.sched.T + a.sched.T - 1) -
-              sched_cta_of(a.sched, (long long)rb * a.sched.T) + 1;
-  slot_lo[1] = a.slot_base_b;
-  slot_n[1] = a.sched_b.P > 0 ? sched_cta_of(a.sched_b, (long long)rb * a.sched_b.T + a.sched_b.T - 1) -
-                                    sched_cta_of(a.sched_b, (long long)rb * a.sched_b.T) + 1
-                              : 0;
-  for (int ps = 0; ps < 2; ++ps)
-    for (int s = slot_lo[ps]; s < slot_lo[ps] + slot_n[ps]; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(a.dz_part + ((int64_t)s * a.rows_pad + lr) * TD + 4 * c4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  // pass A (a.sched, slots from a.slot_base: per column panel the CTAs touching this row block) and, after a
+  // two-phase backward, pass B (one panel)
+  for (int ps = 0; ps < 2; ++ps) {
+    const TcSched& ms = ps == 0 ? a.sched : a.sched_b;
+    if (ms.P <= 0) continue;
+    const int base = ps == 0 ? a.slot_base : a.slot_base_b;
+    for (int pn = 0; pn < ms.NP; ++pn) {
+      const long long u0 = sched_first_unit(ms, pn, rb);
+      const int first = sched_cta_of(ms, u0), last = sched_cta_of(ms, u0 + sched_panel_tiles(ms, pn) - 1);
+      for (int s = base + pn * a.spp; s <= base + pn * a.spp + (last - first); ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(a.dz_part + ((int64_t)s * a.rows_pad + lr) * TD + 4 * c4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
     }
+  }
   const int gi = a.row_offset + lr;
   const float cu = a.scalars[0];
   if (cu != 0.f) {
@@ -1034,7 +1062,7 @@ __global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const _
 // Tuning knobs: read from the environment ONCE, when the library is first used (never on the launch path),
 // so that a plan is a pure function of the problem afterwards.  0 / unset = the built-in choice.
 struct TcKnobs {
-  int fwd_ctas, bwd_ctas, local_ctas, local_free_sms, bwd_local_free_sms;
+  int fwd_ctas, bwd_ctas, local_ctas, local_free_sms, bwd_local_free_sms, bwd_panels;
 };
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -1043,7 +1071,7 @@ int env_int(const char* name, int dflt) {
 const TcKnobs& knobs() {
   static const TcKnobs k = {env_int("SUPCON_TC_FWD_CTAS", 0), env_int("SUPCON_TC_BWD_CTAS", 0),
                             env_int("SUPCON_TC_LOCAL_CTAS", 0), env_int("SUPCON_TC_LOCAL_FREE_SMS", 32),
-                            env_int("SUPCON_TC_BWD_LOCAL_FREE_SMS", 16)};
+                            env_int("SUPCON_TC_BWD_LOCAL_FREE_SMS", 16), env_int("SUPCON_TC_BWD_PANELS", 0)};
   return k;
 }
 
@@ -1051,6 +1079,7 @@ TcSched make_sched(int row_blocks, int col_tiles, int num_sms, int forced_ctas, 
   TcSched sc;
   sc.T = col_tiles;
   sc.U = (long long)row_blocks * col_tiles;
+  sc.RB = row_blocks; sc.NP = 1; sc.Tp = col_tiles;
   // two CTAs' worth of work per SM: the hardware scheduler evens out SM-to-SM speed differences
   // (measured: rank share of N/8 rows 0.714 -> 0.694 ms), as long as a CTA still gets >= 32 tiles
   long long p = forced_ctas;
@@ -1060,6 +1089,17 @@ TcSched make_sched(int row_blocks, int col_tiles, int num_sms, int forced_ctas, 
   if (p < 1) p = 1;
   sc.P = (int)p;
   return sc;
+}
+// most CTAs touching one (panel, row block) run of a panel-ordered list
+int sched_max_slots_panels(const TcSched& sc) {
+  int m = 1;
+  for (int pn = 0; pn < sc.NP; ++pn)
+    for (int rb = 0; rb < sc.RB; ++rb) {
+      const long long u0 = sched_first_unit(sc, pn, rb);
+      const int n = sched_cta_of(sc, u0 + sched_panel_tiles(sc, pn) - 1) - sched_cta_of(sc, u0) + 1;
+      if (n > m) m = n;
+    }
+  return m;
 }
 int sched_max_slots(const TcSched& sc, int row_blocks) {
   int m = 1;
@@ -1116,7 +1156,24 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.fwd_sched = make_sched(pl.fwd_row_blocks, pl.fwd_col_tiles, sms, kn.fwd_ctas);
   pl.bwd_sched = make_sched(pl.row_blocks, pl.bwd_col_tiles, sms, kn.bwd_ctas);
   pl.fwd_slots = sched_max_slots(pl.fwd_sched, pl.fwd_row_blocks);
-  pl.bwd_slots = sched_max_slots(pl.bwd_sched, pl.row_blocks);
+  // Backward beyond L2: with z larger than ~48 MB the CTAs of a wave, each somewhere else in its own column sweep,
+  // stream ALL of z concurrently and the 64-column Z_J tiles miss L2 (measured at N = 186368: backward 25 % slower
+  // per pair).  Ordering the list by column panels of <= ~24 MB keeps the concurrently live part of z near 48 MB.
+  {
+    const size_t z_bytes = (size_t)p->n_total * TD * 2;
+    int np = (int)((z_bytes + (24u << 20) - 1) / (24u << 20));
+    if (z_bytes <= (48u << 20)) np = 1;
+    if (np > 16) np = 16;
+    while (np > 1 && pl.bwd_col_tiles < 64 * np) --np;
+    if (knobs().bwd_panels > 0) np = knobs().bwd_panels;
+    if (np > 1) {
+      pl.bwd_sched.NP = np;
+      pl.bwd_sched.Tp = (pl.bwd_col_tiles + np - 1) / np;
+      while (pl.bwd_sched.NP > 1 && (pl.bwd_sched.NP - 1) * pl.bwd_sched.Tp >= pl.bwd_col_tiles) --pl.bwd_sched.NP;
+    }
+  }
+  pl.bwd_spp = sched_max_slots_panels(pl.bwd_sched);
+  pl.bwd_slots = pl.bwd_sched.NP * pl.bwd_spp;
   // two-phase sweeps (multi-GPU overlap): phase 1 covers the rank's own columns, phase 2 the others
   pl.two_phase = (p->n_rows < p->n_total) && (p->row_offset % 128 == 0) && (p->n_rows % 128 == 0);
   pl.local_ct0 = p->row_offset / 128;
@@ -1196,6 +1253,7 @@ int tc_debug_sched(int T, int P, long long U, int cta, int row_block, long long*
                    int* first_cta, int* last_cta) {
   TcSched sc;
   sc.T = T; sc.P = P; sc.U = U;
+  sc.RB = (int)(U / T); sc.NP = 1; sc.Tp = T;
   *range_begin = sched_begin(sc, cta);
   *range_end = sched_begin(sc, cta + 1);
   *first_cta = sched_cta_of(sc, (long long)row_block * T);
@@ -1477,8 +1535,11 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   a.dz_part = reinterpret_cast<float*>(ws + pl.off_part);
   a.n_total = p->n_total; a.n_pad = pl.n_pad; a.row_offset = p->row_offset; a.n_rows = p->n_rows;
   a.rows_pad = pl.rows_pad; a.sched = pl.bwd_sched;
-  a.sched_b.P = 0; a.sched_b.T = 1; a.sched_b.U = 1; a.slot_base_b = 0;
+  a.sched_b.P = 0; a.sched_b.T = 1; a.sched_b.U = 1; a.sched_b.RB = 1; a.sched_b.NP = 1; a.sched_b.Tp = 1;
+  a.slot_base_b = 0;
   a.ct_base = 0; a.ex_lo = 0x7fffffff; a.ex_len = 0; a.slot_base = 0;
+  a.spp = pl.bwd_spp;
+  if (phase != 0) a.spp = 0;   // the two-phase schedules have one panel each
   if (phase == 1) { a.sched = pl.bwd_sched_local; a.ct_base = pl.bwd_local_ct0; }
   if (phase == 2) {
     a.sched = pl.bwd_sched_remote; a.ex_lo = pl.bwd_local_ct0; a.ex_len = pl.bwd_local_cts;
