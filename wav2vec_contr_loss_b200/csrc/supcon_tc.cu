@@ -1157,11 +1157,13 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.bwd_sched = make_sched(pl.row_blocks, pl.bwd_col_tiles, sms, kn.bwd_ctas);
   pl.fwd_slots = sched_max_slots(pl.fwd_sched, pl.fwd_row_blocks);
   // Backward beyond L2: with z larger than ~48 MB the CTAs of a wave, each somewhere else in its own column sweep,
-  // stream ALL of z concurrently and the 64-column Z_J tiles miss L2 (measured at N = 186368: backward 25 % slower
-  // per pair).  Ordering the list by column panels of <= ~24 MB keeps the concurrently live part of z near 48 MB.
+  // stream ALL of z concurrently and the 64-column Z_J tiles miss L2 (measured at N = 186368, a rank's 23296 rows:
+  // backward 4.21 ms = 25 % slower per pair than at N = 65536).  Ordering the list by column panels of <= 48 MB
+  // keeps the concurrently live part of z inside L2: 2 panels 3.17 ms (the N = 65536 rate), 4 panels 3.61 ms,
+  // 8 panels 3.88 ms (more partial records and shorter runs) -- so as few panels as fit.
   {
     const size_t z_bytes = (size_t)p->n_total * TD * 2;
-    int np = (int)((z_bytes + (24u << 20) - 1) / (24u << 20));
+    int np = (int)((z_bytes + (48u << 20) - 1) / (48u << 20));
     if (z_bytes <= (48u << 20)) np = 1;
     if (np > 16) np = 16;
     while (np > 1 && pl.bwd_col_tiles < 64 * np) --np;
