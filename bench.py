@@ -587,14 +587,25 @@ def main():
             host_ms = eager_ms(one, reps_)
             dev_ms = time_graph(Stepper(one), reps_, do_flush=False)
             return {"device_us": round(1e3 * dev_ms, 2), "host_inclusive_us": round(1e3 * host_ms, 2)}
+        def cabi_case(nn_):     # supcon_loss_and_grad through the C-ABI wrapper: the kernel(s) alone, no autograd glue
+            zc, yc = synth(nn_, d, torch.float32)
+            zc, yc = zc.to(dev), yc.to(dev).to(torch.int32)
+            pr = Fn.make_problem(nn_, d, _cabi.F32, tau=args.tau, similarity=sim_id, topk=15, alpha=0.0)
+            one = lambda: Fn.loss_and_grad(zc, yc, pr, want_grad=True)
+            for _ in range(3):
+                one()
+            return round(1e3 * time_graph(Stepper(one), 50, do_flush=False), 2)
         extras = {
+            "n64_cabi_single_launch_us": cabi_case(64),      # the <30 us target of the north_star: one cluster launch
+            "n256_cabi_single_launch_us": cabi_case(256),    # the reference's default batch (stage1_config.py:22), fp32
             "n64_fwd_bwd_us": module_case(64, torch.float32, "cosine", 0.0, 15, 0.0, 50),               # configs[0]
             "n64_geodesic_uniformity_us": module_case(64, torch.float32, "geodesic", 0.05, 15, 0.0, 50),  # configs[1]
             "n1024_mined_f32_us": module_case(1024, torch.float32, "cosine", 0.0, 15, 0.5, 20),           # configs[2]
             "n1024_mined_bf16_us": module_case(1024, torch.bfloat16, "cosine", 0.0, 15, 0.5, 20),
             "n65536_mined_bf16_us": module_case(65536, torch.bfloat16, "cosine", 0.0, 15, 0.5, 5),
-            "note": "fwd+bwd through SupConBinaryLoss + autograd; device_us = one CUDA-graph replay (CUDA events), "
-                    "host_inclusive_us = eager Python call, wall clock incl. launch overhead",
+            "note": "fwd+bwd through SupConBinaryLoss + autograd (label cast, the loss kernels, grad_out fill and "
+                    "scaling); device_us = one CUDA-graph replay (CUDA events), host_inclusive_us = eager Python call, "
+                    "wall clock incl. launch overhead; *_cabi_* = supcon_loss_and_grad alone, graph replay",
         }
         launches["count"] = n_before
 
