@@ -48,6 +48,36 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / ALU pipes (no MUFU), for x in (-126, 127): Cody-Waite split x = n + f with n = floor(x) taken
+// from the low mantissa bits of x + 1.5 * 2^23 (rounded toward -inf), 2^f on [0, 1) by the degree-4 minimax
+// polynomial (relative error 2.7e-6, fp32 Horner included), 2^n added into the exponent field.  Built to take a
+// fixed fraction of the forward's exponentials off the MUFU unit (at d = 256 a 128 x 128 tile costs the tensor
+// pipe and the MUFU unit the same ~1024 cycles per SM); see poly_elem for what the measurement said.
+// The exponents of this path lie in [-2 M log2(e) / tau, ~1] with M / tau <= 40 (tc_supported / m_limit), i.e.
+// above -116: no clamp is needed.  Which elements take this route depends only on the column index (mod 8), so
+// the result does not depend on how rows or columns are split over CTAs or ranks.
+__device__ __forceinline__ float ex2_poly(float x) {
+  constexpr float MAGIC = 12582912.f;   // 1.5 * 2^23
+  float r;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(MAGIC));
+  const float f = x - (r - MAGIC);      // in [0, 1)
+  float p = 0.013534167781472206f;
+  p = fmaf(p, f, 0.052011460065841675f);
+  p = fmaf(p, f, 0.2414427548646927f);
+  p = fmaf(p, f, 0.6930038332939148f);
+  p = fmaf(p, f, 1.0000026226043701f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+// element e of a 32-column chunk takes the polynomial route when POLY says so: 4 = every fourth, 8 = every
+// eighth, 2 = every second, 0 = none.  MEASURED (profiles/r02_fwd_poly_ab.md, N = 65536): forward 1.573 ms with
+// none, 1.636 / 1.763 / 2.041 ms with 1/8, 1/4, 1/2 of the exponentials here -- the sweep is bound by the
+// dependent instruction stream of its two softmax warps per scheduler, not by MUFU throughput, and the
+// polynomial's eight dependent FMA-pipe instructions lengthen exactly that.  So the default is 0; the 1/4
+// variant stays selectable (SUPCON_TC_FWD_POLY=4) to reproduce the measurement.
+template <int POLY>
+__device__ __forceinline__ constexpr bool poly_elem(int e) {
+  return POLY == 2 ? (e & 1) == 1 : POLY == 4 ? (e & 3) == 3 : POLY == 8 ? (e & 7) == 7 : false;
+}
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -327,7 +357,7 @@ __device__ __noinline__ MineState mine_candidates(int sim, uint32_t taddr_chunk,
   return ms;
 }
 
-template <int SIM, bool UNI, bool MINE, bool MASKED>
+template <int SIM, bool UNI, bool MINE, bool MASKED, int POLY>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int gi, int n_total, int lab_r,
                                           float nrm_r, const int32_t* __restrict__ lab_s,
                                           const float* __restrict__ nrm_s, float c1, float c0, float ut2,
@@ -346,7 +376,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
     for (int e = 0; e < 4; ++e) {
       const float c = __uint_as_float(r[4 * q + e]);
       const float s = (SIM == SUPCON_GEODESIC) ? geodesic_sim_fast(c) : c;
-      float ex = ex2f(fmaf(s, c1, c0));
+      float ex = poly_elem<POLY>(4 * q + e) ? ex2_poly(fmaf(s, c1, c0)) : ex2f(fmaf(s, c1, c0));
       bool pos = labs[e] == lab_r;
       bool neg = !pos;
       if (MASKED) {
@@ -411,7 +441,7 @@ __device__ __forceinline__ void load_rows_to_tmem(const __nv_bfloat16* __restric
 // releases the TMEM buffer at once (the next MMA into it overlaps the exp work) and then reduces
 // from registers.  All pipeline barriers are indexed by a running tile counter, so segments
 // follow each other without draining the TMA ring.
-template <int SIM, bool UNI, bool MINE>
+template <int SIM, bool UNI, bool MINE, int POLY>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
                                                              const __nv_bfloat16* __restrict__ z, TcFwdArgs a) {
   constexpr int BN = 128;
@@ -553,15 +583,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
         const int32_t* lab_s = lab_ring[slot];
         const float* nrm_s = nrm_ring[UNI ? slot : 0];
         if (masked) {
-          fwd_chunk<SIM, UNI, MINE, true>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
-          fwd_chunk<SIM, UNI, MINE, true>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
-          fwd_chunk<SIM, UNI, MINE, true>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
-          fwd_chunk<SIM, UNI, MINE, true>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+          fwd_chunk<SIM, UNI, MINE, true, POLY>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
+          fwd_chunk<SIM, UNI, MINE, true, POLY>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
+          fwd_chunk<SIM, UNI, MINE, true, POLY>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
+          fwd_chunk<SIM, UNI, MINE, true, POLY>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
         } else {
-          fwd_chunk<SIM, UNI, MINE, false>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
-          fwd_chunk<SIM, UNI, MINE, false>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
-          fwd_chunk<SIM, UNI, MINE, false>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
-          fwd_chunk<SIM, UNI, MINE, false>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+          fwd_chunk<SIM, UNI, MINE, false, POLY>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
+          fwd_chunk<SIM, UNI, MINE, false, POLY>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
+          fwd_chunk<SIM, UNI, MINE, false, POLY>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
+          fwd_chunk<SIM, UNI, MINE, false, POLY>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
         }
         if (MINE) {   // candidates re-read S from tensor memory: release the buffer only now
           ptx::tc_fence_before_sync();
@@ -1063,6 +1093,7 @@ __global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const _
 // so that a plan is a pure function of the problem afterwards.  0 / unset = the built-in choice.
 struct TcKnobs {
   int fwd_ctas, bwd_ctas, local_ctas, local_free_sms, bwd_local_free_sms, bwd_panels;
+  int fwd_poly;   // 4: a quarter of the forward's exponentials evaluated off the MUFU unit (A/B only); else none
 };
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -1071,7 +1102,8 @@ int env_int(const char* name, int dflt) {
 const TcKnobs& knobs() {
   static const TcKnobs k = {env_int("SUPCON_TC_FWD_CTAS", 0), env_int("SUPCON_TC_BWD_CTAS", 0),
                             env_int("SUPCON_TC_LOCAL_CTAS", 0), env_int("SUPCON_TC_LOCAL_FREE_SMS", 32),
-                            env_int("SUPCON_TC_BWD_LOCAL_FREE_SMS", 16), env_int("SUPCON_TC_BWD_PANELS", 0)};
+                            env_int("SUPCON_TC_BWD_LOCAL_FREE_SMS", 16), env_int("SUPCON_TC_BWD_PANELS", 0),
+                            env_int("SUPCON_TC_FWD_POLY", -1)};
   return k;
 }
 
@@ -1274,19 +1306,25 @@ bool tc_supported(const supcon_problem_t* p) {
   return true;
 }
 
-template <int SIM, bool UNI, bool MINE>
+constexpr int FWD_POLY_DEFAULT = 0;
+template <int SIM, bool UNI, bool MINE, int POLY>
 static cudaError_t launch_fwd(const CUtensorMap& tm, const __nv_bfloat16* z, const TcFwdArgs& a, int ctas, size_t smem,
                               cudaStream_t st) {
   cudaError_t e =
-      cudaFuncSetAttribute(tc_fwd_kernel<SIM, UNI, MINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(tc_fwd_kernel<SIM, UNI, MINE, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_fwd_kernel<SIM, UNI, MINE><<<ctas, NTHREADS, smem, st>>>(tm, z, a);
+  tc_fwd_kernel<SIM, UNI, MINE, POLY><<<ctas, NTHREADS, smem, st>>>(tm, z, a);
   return cudaGetLastError();
 }
 template <int SIM, bool UNI>
 static cudaError_t launch_fwd_m(bool mine, const CUtensorMap& tm, const __nv_bfloat16* z, const TcFwdArgs& a, int ctas,
                                 size_t smem, cudaStream_t st) {
-  return mine ? launch_fwd<SIM, UNI, true>(tm, z, a, ctas, smem, st) : launch_fwd<SIM, UNI, false>(tm, z, a, ctas, smem, st);
+  // mining: the sorted inserts, not the exponentials, bound that sweep -> all exponentials stay on the MUFU unit
+  if (mine) return launch_fwd<SIM, UNI, true, 0>(tm, z, a, ctas, smem, st);
+  const int poly = knobs().fwd_poly < 0 ? FWD_POLY_DEFAULT : knobs().fwd_poly;
+  // the polynomial share exists for the headline variant only (A/B measurement: profiles/r02_fwd_poly_ab.md)
+  if (SIM == SUPCON_COSINE && !UNI && poly == 4) return launch_fwd<SUPCON_COSINE, false, false, 4>(tm, z, a, ctas, smem, st);
+  return launch_fwd<SIM, UNI, false, FWD_POLY_DEFAULT>(tm, z, a, ctas, smem, st);
 }
 
 bool tc_two_phase(const supcon_problem_t* p) { return tc_supported(p) && tc_plan(p).two_phase; }
