@@ -40,7 +40,12 @@ namespace {
 constexpr int TBM = 128;                  // rows per CTA
 constexpr int TD = 256;                   // embedding width handled here
 constexpr int NBOX = TD / 64;             // 64-column (128-byte) TMA boxes per row
-constexpr int NTHREADS = 320;
+// threads per CTA: TMA producer warp + MMA issuer warp + 8 * NCH softmax / H warps, where NCH = how many threads
+// share one row of a tile (each takes 1/NCH of its columns).  NCH = 1: one thread per row, the whole 128-column
+// (forward) / 64-column (backward) tile row in registers, 168 registers per thread.  NCH = 2 (round 2): twice the
+// warps per scheduler with half the tile row each -- the sweeps are bound by the latency of each warp's dependent
+// instruction stream (profiles/r02_ncu_mined_fwd.md, r02_fwd_poly_ab.md), which more warps hide.
+__host__ __device__ constexpr int tc_threads(int nch) { return 64 + 256 * nch; }
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -417,11 +422,12 @@ __device__ __forceinline__ int fwd_col_tile(const TcFwdArgs& a, int ct) {
 
 // Z rows -> tensor memory as the A operand of tcgen05.mma (kind::f16, A from TMEM):
 // lane = row, 32-bit column m holds the bf16 pair (z[2m], z[2m+1]).
+// Chunks [c_lo, c_hi) of 64 elements: the threads sharing a row split them.
 __device__ __forceinline__ void load_rows_to_tmem(const __nv_bfloat16* __restrict__ z, int gi, int n_total,
-                                                  uint32_t taddr) {
+                                                  uint32_t taddr, int c_lo = 0, int c_hi = TD / 64) {
   const uint4* src = reinterpret_cast<const uint4*>(z + (int64_t)min(gi, n_total - 1) * TD);
 #pragma unroll 1
-  for (int c = 0; c < TD / 64; ++c) {
+  for (int c = c_lo; c < c_hi; ++c) {
     uint32_t w[32];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -441,10 +447,12 @@ __device__ __forceinline__ void load_rows_to_tmem(const __nv_bfloat16* __restric
 // releases the TMEM buffer at once (the next MMA into it overlaps the exp work) and then reduces
 // from registers.  All pipeline barriers are indexed by a running tile counter, so segments
 // follow each other without draining the TMA ring.
-template <int SIM, bool UNI, bool MINE, int POLY>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                             const __nv_bfloat16* __restrict__ z, TcFwdArgs a) {
+template <int SIM, bool UNI, bool MINE, int POLY, int NCH>
+__global__ void __launch_bounds__(tc_threads(NCH), 1) tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                    const __nv_bfloat16* __restrict__ z, TcFwdArgs a) {
+  static_assert(NCH == 1 || (NCH == 2 && !MINE), "the top-K lists are kept by one thread per row");
   constexpr int BN = 128;
+  constexpr int CW = BN / NCH;                       // tile columns per thread
   constexpr uint32_t BOX_BYTES = 128 * 128;          // 128 rows x 128 B
   constexpr uint32_t TILE_BYTES = NBOX * BOX_BYTES;  // 64 KB
   constexpr int STAGES = MINE ? 2 : 3;               // mining: the third stage's 64 KB hold the top-K lists
@@ -460,15 +468,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) int32_t lab_ring[RING][BN];
   __shared__ __align__(16) float nrm_ring[UNI ? RING : 1][BN];
+  __shared__ __align__(16) float4 comb[NCH == 2 ? 2 : 1][NCH == 2 ? TBM : 1];   // row sums of the second column half
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const TcSched sc = a.sched;
   const long long u_begin = sched_begin(sc, blockIdx.x), u_end = sched_begin(sc, blockIdx.x + 1);
 
   if (tid == 0) {
-    ptx::mbar_init(&bar_a, 256);
+    ptx::mbar_init(&bar_a, 256 * NCH);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_tfull[b], 1); ptx::mbar_init(&bar_tempty[b], 128); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_tfull[b], 1); ptx::mbar_init(&bar_tempty[b], 128 * NCH); }
     for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
     ptx::fence_mbar_init();
     ptx::tma_prefetch_desc(&tmap);
@@ -535,15 +544,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
       }
     }
   } else {
-    // ===== softmax warpgroups: warps 2-5 own row block a, warps 6-9 row block b =====
-    const int wg = (warp - 2) >> 2;
+    // ===== softmax warps: groups of four (one per TMEM lane quarter); group s = (warp - 2) / 4 owns row block
+    //       s & 1 (a / b) and columns [CW * (s >> 1), + CW) of every tile =====
+    const int wg = ((warp - 2) >> 2) & 1, ch = (warp - 2) >> 3;
     const int lrow = 32 * (warp & 3) + lane;  // TMEM lane == row within the block
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     // top-K lists: [256 rows][32] values then [256 rows][32] indices; this warp's 32 rows start at wl_v / wl_i
-    float* wl_v = reinterpret_cast<float*>(sZJ + STAGES * TILE_BYTES) + (warp - 2) * 32 * LIST_STRIDE;
-    int* wl_i = reinterpret_cast<int*>(sZJ + STAGES * TILE_BYTES + 256 * LIST_STRIDE * 4) + (warp - 2) * 32 * LIST_STRIDE;
+    float* wl_v = reinterpret_cast<float*>(sZJ + STAGES * TILE_BYTES) + ((warp - 2) & 7) * 32 * LIST_STRIDE;
+    int* wl_i = reinterpret_cast<int*>(sZJ + STAGES * TILE_BYTES + 256 * LIST_STRIDE * 4) + ((warp - 2) & 7) * 32 * LIST_STRIDE;
     const int K = a.kcap;
-    const uint32_t taddr = tmem + lane_addr + TM_S + wg * BN;
+    const uint32_t taddr = tmem + lane_addr + TM_S + wg * BN + ch * CW;
     // exponent offset of this launch: -M/tau * log2(e) with the fixed maximum as of this phase's prep kernel
     const float c0 = -a.c1 * fixmax_from_bits(*a.nrm2_max, a.m_limit);
     int g = 0;
@@ -554,7 +564,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
       const int gi = rblk0 + lrow;
       // A_g may be rewritten: every MMA that read it has completed (this warpgroup saw the tfull of
       // the previous segment's last tile)
-      load_rows_to_tmem(z, gi, a.n_total, tmem + lane_addr + TM_A + wg * (TD / 2));
+      load_rows_to_tmem(z, gi, a.n_total, tmem + lane_addr + TM_A + wg * (TD / 2), ch * (TD / 64 / NCH),
+                        (ch + 1) * (TD / 64 / NCH));
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&bar_a);
       const int lab_r = a.lab_pad[min(gi, a.n_pad - 1)];
@@ -569,36 +580,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_fwd_kernel(const __grid_consta
         ptx::mbar_wait(&bar_col[slot], (g / RING) & 1);
         ptx::mbar_wait(&bar_tfull[wg], g & 1);
         ptx::tc_fence_after_sync();
-        uint32_t r0[32], r1[32], r2[32], r3[32];
+        uint32_t r0[32], r1[32], r2[NCH == 1 ? 32 : 1], r3[NCH == 1 ? 32 : 1];
         ptx::tmem_ld32(taddr, r0);
         ptx::tmem_ld32(taddr + 32, r1);
-        ptx::tmem_ld32(taddr + 64, r2);
-        ptx::tmem_ld32(taddr + 96, r3);
+        if constexpr (NCH == 1) {
+          ptx::tmem_ld32(taddr + 64, r2);
+          ptx::tmem_ld32(taddr + 96, r3);
+        }
         ptx::tmem_ld_wait();
         if (!MINE) {
           ptx::tc_fence_before_sync();
           ptx::mbar_arrive(&bar_tempty[wg]);   // S_g is free again: the next MMA overlaps the work below
         }
         const bool masked = (col0 + BN > a.n_total) || (col0 < rblk0 + TBM && rblk0 < col0 + BN);
-        const int32_t* lab_s = lab_ring[slot];
-        const float* nrm_s = nrm_ring[UNI ? slot : 0];
+        const int cc = ch * CW;                // first tile column of this thread
+        const int32_t* lab_s = lab_ring[slot] + cc;
+        const float* nrm_s = nrm_ring[UNI ? slot : 0] + cc;
         if (masked) {
-          fwd_chunk<SIM, UNI, MINE, true, POLY>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
-          fwd_chunk<SIM, UNI, MINE, true, POLY>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
-          fwd_chunk<SIM, UNI, MINE, true, POLY>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
-          fwd_chunk<SIM, UNI, MINE, true, POLY>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+          fwd_chunk<SIM, UNI, MINE, true, POLY>(r0, col0 + cc, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
+          fwd_chunk<SIM, UNI, MINE, true, POLY>(r1, col0 + cc + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
+          if constexpr (NCH == 1) {
+            fwd_chunk<SIM, UNI, MINE, true, POLY>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
+            fwd_chunk<SIM, UNI, MINE, true, POLY>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+          }
         } else {
-          fwd_chunk<SIM, UNI, MINE, false, POLY>(r0, col0, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
-          fwd_chunk<SIM, UNI, MINE, false, POLY>(r1, col0 + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
-          fwd_chunk<SIM, UNI, MINE, false, POLY>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
-          fwd_chunk<SIM, UNI, MINE, false, POLY>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+          fwd_chunk<SIM, UNI, MINE, false, POLY>(r0, col0 + cc, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
+          fwd_chunk<SIM, UNI, MINE, false, POLY>(r1, col0 + cc + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
+          if constexpr (NCH == 1) {
+            fwd_chunk<SIM, UNI, MINE, false, POLY>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
+            fwd_chunk<SIM, UNI, MINE, false, POLY>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+          }
         }
         if (MINE) {   // candidates re-read S from tensor memory: release the buffer only now
           ptx::tc_fence_before_sync();
           ptx::mbar_arrive(&bar_tempty[wg]);
         }
       }
-      if (gi < a.row_offset + a.n_rows) {
+      if constexpr (NCH == 2) {
+        // the two threads of a row add their halves: the upper half goes through shared memory.  No second barrier
+        // is needed before comb is written again: that happens after a tile of the NEXT segment, whose MMAs wait
+        // for every thread's arrival on bar_a, which the readers below give after they have read.
+        if (ch == 1) comb[wg][lrow] = make_float4(st.sum_all, st.sum_pos_s, st.wsum, st.sum_pos_e);
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory");
+        if (ch == 0) {
+          const float4 o = comb[wg][lrow];
+          st.sum_all += o.x; st.sum_pos_s += o.y; st.wsum += o.z; st.sum_pos_e += o.w;
+        }
+      }
+      if (ch == 0 && gi < a.row_offset + a.n_rows) {
         const int slot_out = a.slot_base + (int)blockIdx.x - sched_cta_of(sc, (long long)rb * sc.T);
         const int64_t rec = (int64_t)slot_out * a.rows_pad + (gi - a.row_offset);
         float* out = a.part + rec * 8;
@@ -821,10 +850,12 @@ __device__ __forceinline__ int bwd_col_tile(const TcBwdArgs& a, int ct) {
 // what holds the pipe at ~75 %.  What the variants share is the shared-memory traffic per tile: 32 KB read by
 // the S MMAs + 32 KB by the dZ MMAs + 32 KB written by TMA = 94 B/clk of the 128 B/clk port; sharing Z_J
 // between two CTAs (cta_group::2) is the remaining lever.
-template <int SIM, bool UNI, bool MINE>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapJ,
-                                                             const __nv_bfloat16* __restrict__ z, TcBwdArgs a) {
+template <int SIM, bool UNI, bool MINE, int NCH>
+__global__ void __launch_bounds__(tc_threads(NCH), 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapJ,
+                                                                    const __nv_bfloat16* __restrict__ z, TcBwdArgs a) {
+  static_assert(NCH == 1 || NCH == 2, "one or two threads per tile row");
   constexpr int BN = 64;
+  constexpr int CW = BN / NCH;                         // tile columns per thread
   constexpr int STAGES = 6;
   constexpr int RING = STAGES;
   constexpr uint32_t BOXJ_BYTES = BN * 128;            // Z_J boxes: 64 rows x 128 B
@@ -846,11 +877,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
   const long long u_begin = sched_begin(sc, blockIdx.x), u_end = sched_begin(sc, blockIdx.x + 1);
 
   if (tid == 0) {
-    ptx::mbar_init(&bar_a, 128);
+    ptx::mbar_init(&bar_a, 128 * NCH);
     ptx::mbar_init(&bar_done, 1);
-    ptx::mbar_init(&bar_dzfree, 256);
+    ptx::mbar_init(&bar_dzfree, 256 * NCH);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_hfull[b], 128); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&bar_sfull[b], 1); ptx::mbar_init(&bar_hfull[b], 128 * NCH); }
     for (int b = 0; b < RING; ++b) ptx::mbar_init(&bar_col[b], 1);
     ptx::fence_mbar_init();
     ptx::tma_prefetch_desc(&tmapJ);
@@ -941,7 +972,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
             const uint32_t b0 = ptx::smem_u32(sZJ + st * TILEJ_BYTES);
 #pragma unroll
             for (int kk = 0; kk < BN / 16; ++kk) {
-              ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + 8 * kk,
+              // H of tile columns [16 kk, 16 kk + 16): 8 packed columns; each thread of a row writes its part of
+              // H over the start of ITS OWN part of S (NCH = 2: columns 0..15 and 32..47 of the buffer)
+              const uint32_t hcol = NCH == 1 ? 8 * kk : (kk >> 1) * CW + (kk & 1) * 8;
+              ptx::mma_ts(tmem + TM_DZ, tmem + TM_S + buf * BN + hcol,
                           ptx::smem_desc_sw128(b0 + kk * 16 * 128, BOXJ_BYTES, 1024), idesc_dz, (t > 1 || kk > 0));
             }
             ptx::mma_commit(&bar_empty[st]);
@@ -953,13 +987,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       }
     }
   } else {
-    // ===== H warpgroups: warpgroup w takes the tiles with (running index & 1) == w (S/H buffer w) =====
-    const int wg = (warp - 2) >> 2;
+    // ===== H warps in groups of four (one per TMEM lane quarter): group s = (warp - 2) / 4 takes the tiles with
+    //       (running index & 1) == (s & 1) (S/H buffer s & 1) and, of those, columns [CW * (s >> 1), + CW) =====
+    const int wg = ((warp - 2) >> 2) & 1, ch = (warp - 2) >> 3;
     const int lrow = 32 * (warp & 3) + lane;
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     const float cu = UNI ? a.scalars[0] : 0.f;
     const float c0 = a.scalars[1];   // -M/tau * log2(e), M = the forward's fixed maximum
-    const uint32_t sbuf = tmem + lane_addr + TM_S + wg * BN;
+    const uint32_t sbuf = tmem + lane_addr + TM_S + wg * BN + ch * CW;
     int g0 = 0, seg = 0;
     for (long long u = u_begin; u < u_end; ++seg) {
       const SchedRun sr = sched_decode(sc, u);
@@ -969,7 +1004,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       const int gi = row0 + lrow;
       if (wg == 0) {
         // the previous segment's MMAs (readers of Z_I) are complete: both warpgroups waited on bar_done
-        load_rows_to_tmem(z, gi, a.n_total, tmem + lane_addr + TM_A);
+        load_rows_to_tmem(z, gi, a.n_total, tmem + lane_addr + TM_A, ch * (TD / 64 / NCH), (ch + 1) * (TD / 64 / NCH));
         ptx::tc_fence_before_sync();
         ptx::mbar_arrive(&bar_a);
       }
@@ -986,27 +1021,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
         ptx::mbar_wait(&bar_col[slot], (g / RING) & 1);
         ptx::mbar_wait(&bar_sfull[wg], buse & 1);
         ptx::tc_fence_after_sync();
-        uint32_t r0[32], r1[32];
+        uint32_t r0[32], r1[NCH == 1 ? 32 : 1];
         ptx::tmem_ld32(sbuf, r0);
-        ptx::tmem_ld32(sbuf + 32, r1);
+        if constexpr (NCH == 1) ptx::tmem_ld32(sbuf + 32, r1);
         ptx::tmem_ld_wait();
-        uint32_t hw[32];
+        uint32_t hw[CW / 2];
         uint32_t (&h0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[0]);
-        uint32_t (&h1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[16]);
+        const int cc = ch * CW;                // first tile column of this thread
         ColVecs cv0, cv1;
-        cv0.lab = lab_ring[slot]; cv0.A = colA_ring[slot]; cv0.B = colB_ring[slot]; cv0.nrm = nrm_ring[UNI ? slot : 0];
-        cv0.Am = colAm_ring[MINE ? slot : 0]; cv0.thr = thr_ring[MINE ? slot : 0]; cv0.thr_idx = thridx_ring[MINE ? slot : 0];
+        cv0.lab = lab_ring[slot] + cc; cv0.A = colA_ring[slot] + cc; cv0.B = colB_ring[slot] + cc;
+        cv0.nrm = nrm_ring[UNI ? slot : 0] + cc;
+        cv0.Am = colAm_ring[MINE ? slot : 0] + cc; cv0.thr = thr_ring[MINE ? slot : 0] + cc;
+        cv0.thr_idx = thridx_ring[MINE ? slot : 0] + cc;
         cv1.lab = cv0.lab + 32; cv1.A = cv0.A + 32; cv1.B = cv0.B + 32; cv1.nrm = cv0.nrm + 32;
         cv1.Am = cv0.Am + 32; cv1.thr = cv0.thr + 32; cv1.thr_idx = cv0.thr_idx + 32;
         const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
         if (masked) {
-          bwd_chunk<SIM, UNI, MINE, true, 8>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv0, rm, a);
-          bwd_chunk<SIM, UNI, MINE, true, 8>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv1, rm, a);
+          bwd_chunk<SIM, UNI, MINE, true, 8>(r0, h0, col0 + cc, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv0, rm, a);
         } else {
-          bwd_chunk<SIM, UNI, MINE, false, 8>(r0, h0, col0, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv0, rm, a);
-          bwd_chunk<SIM, UNI, MINE, false, 8>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv1, rm, a);
+          bwd_chunk<SIM, UNI, MINE, false, 8>(r0, h0, col0 + cc, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv0, rm, a);
         }
-        ptx::tmem_st32(sbuf, hw);            // H(t): 64 bf16 = 32 packed columns over S(t)
+        if constexpr (NCH == 1) {
+          uint32_t (&h1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[16]);
+          if (masked) {
+            bwd_chunk<SIM, UNI, MINE, true, 8>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv1, rm, a);
+          } else {
+            bwd_chunk<SIM, UNI, MINE, false, 8>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv1, rm, a);
+          }
+          ptx::tmem_st32(sbuf, hw);          // H(t): 64 bf16 = 32 packed columns over S(t)
+        } else {
+          ptx::tmem_st16(sbuf, hw);          // this thread's 32 bf16 = 16 packed columns over ITS part of S(t)
+        }
         ptx::tmem_st_wait();
         ptx::tc_fence_before_sync();
         ptx::mbar_arrive(&bar_hfull[wg]);
@@ -1018,11 +1063,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const __grid_consta
       // one partial record per (panel, CTA touching this row block within the panel)
       const int slot_out = a.slot_base + sr.panel * a.spp + (int)blockIdx.x -
                            sched_cta_of(sc, sched_first_unit(sc, sr.panel, rb));
-      float* outp = a.dz_part + ((int64_t)slot_out * a.rows_pad + (gi - a.row_offset)) * TD + 128 * wg;
+      // dZ columns of this thread: 128 / NCH of them, starting at
+      const int dzc = 128 * wg + (128 / NCH) * ch;
+      float* outp = a.dz_part + ((int64_t)slot_out * a.rows_pad + (gi - a.row_offset)) * TD + dzc;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 4 / NCH; ++c) {
         uint32_t r[32];
-        ptx::tmem_ld32(tmem + lane_addr + TM_DZ + 128 * wg + 32 * c, r);
+        ptx::tmem_ld32(tmem + lane_addr + TM_DZ + dzc + 32 * c, r);
         ptx::tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
@@ -1094,6 +1141,7 @@ __global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const _
 struct TcKnobs {
   int fwd_ctas, bwd_ctas, local_ctas, local_free_sms, bwd_local_free_sms, bwd_panels;
   int fwd_poly;   // 4: a quarter of the forward's exponentials evaluated off the MUFU unit (A/B only); else none
+  int fwd_nch, bwd_nch;   // threads per tile row (1 or 2; 0 = built-in choice), see tc_threads()
 };
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -1103,7 +1151,8 @@ const TcKnobs& knobs() {
   static const TcKnobs k = {env_int("SUPCON_TC_FWD_CTAS", 0), env_int("SUPCON_TC_BWD_CTAS", 0),
                             env_int("SUPCON_TC_LOCAL_CTAS", 0), env_int("SUPCON_TC_LOCAL_FREE_SMS", 32),
                             env_int("SUPCON_TC_BWD_LOCAL_FREE_SMS", 16), env_int("SUPCON_TC_BWD_PANELS", 0),
-                            env_int("SUPCON_TC_FWD_POLY", -1)};
+                            env_int("SUPCON_TC_FWD_POLY", -1), env_int("SUPCON_TC_FWD_NCH", 0),
+                            env_int("SUPCON_TC_BWD_NCH", 0)};
   return k;
 }
 
@@ -1307,24 +1356,34 @@ bool tc_supported(const supcon_problem_t* p) {
 }
 
 constexpr int FWD_POLY_DEFAULT = 0;
-template <int SIM, bool UNI, bool MINE, int POLY>
+// Threads per tile row, measured at N = 65536 (profiles/r02_nch_ab.md): the unmined forward gains 4 % from two
+// (1.663 -> 1.595 ms), the mined backward 13 % (6.93 -> 6.01 ms: its membership tests make it issue-bound and more
+// warps fill the slots); the unmined backward gets SLOWER and unsteady with two (3.11 -> 3.36-3.51 ms median).
+constexpr int FWD_NCH_DEFAULT = 2, BWD_NCH_DEFAULT = 1, BWD_MINE_NCH_DEFAULT = 2;
+template <int SIM, bool UNI, bool MINE, int POLY, int NCH>
 static cudaError_t launch_fwd(const CUtensorMap& tm, const __nv_bfloat16* z, const TcFwdArgs& a, int ctas, size_t smem,
                               cudaStream_t st) {
-  cudaError_t e =
-      cudaFuncSetAttribute(tc_fwd_kernel<SIM, UNI, MINE, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<SIM, UNI, MINE, POLY, NCH>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_fwd_kernel<SIM, UNI, MINE, POLY><<<ctas, NTHREADS, smem, st>>>(tm, z, a);
+  tc_fwd_kernel<SIM, UNI, MINE, POLY, NCH><<<ctas, tc_threads(NCH), smem, st>>>(tm, z, a);
   return cudaGetLastError();
 }
 template <int SIM, bool UNI>
 static cudaError_t launch_fwd_m(bool mine, const CUtensorMap& tm, const __nv_bfloat16* z, const TcFwdArgs& a, int ctas,
                                 size_t smem, cudaStream_t st) {
   // mining: the sorted inserts, not the exponentials, bound that sweep -> all exponentials stay on the MUFU unit
-  if (mine) return launch_fwd<SIM, UNI, true, 0>(tm, z, a, ctas, smem, st);
+  // (and its top-K lists are kept by one thread per row)
+  if (mine) return launch_fwd<SIM, UNI, true, 0, 1>(tm, z, a, ctas, smem, st);
   const int poly = knobs().fwd_poly < 0 ? FWD_POLY_DEFAULT : knobs().fwd_poly;
+  const int nch = knobs().fwd_nch == 1 || knobs().fwd_nch == 2 ? knobs().fwd_nch : FWD_NCH_DEFAULT;
   // the polynomial share exists for the headline variant only (A/B measurement: profiles/r02_fwd_poly_ab.md)
-  if (SIM == SUPCON_COSINE && !UNI && poly == 4) return launch_fwd<SUPCON_COSINE, false, false, 4>(tm, z, a, ctas, smem, st);
-  return launch_fwd<SIM, UNI, false, FWD_POLY_DEFAULT>(tm, z, a, ctas, smem, st);
+  if (SIM == SUPCON_COSINE && !UNI && poly == 4) {
+    if (nch == 2) return launch_fwd<SUPCON_COSINE, false, false, 4, 2>(tm, z, a, ctas, smem, st);
+    return launch_fwd<SUPCON_COSINE, false, false, 4, 1>(tm, z, a, ctas, smem, st);
+  }
+  if (nch == 2) return launch_fwd<SIM, UNI, false, FWD_POLY_DEFAULT, 2>(tm, z, a, ctas, smem, st);
+  return launch_fwd<SIM, UNI, false, FWD_POLY_DEFAULT, 1>(tm, z, a, ctas, smem, st);
 }
 
 bool tc_two_phase(const supcon_problem_t* p) { return tc_supported(p) && tc_plan(p).two_phase; }
@@ -1515,19 +1574,25 @@ int tc_forward_pass(const supcon_problem_t* p, const void* z_all, const int32_t*
   return 0;
 }
 
-template <int SIM, bool UNI, bool MINE>
+template <int SIM, bool UNI, bool MINE, int NCH>
 static cudaError_t launch_bwd(const CUtensorMap& tmJ, const __nv_bfloat16* z, const TcBwdArgs& a, int ctas, size_t smem,
                               cudaStream_t st) {
-  cudaError_t e =
-      cudaFuncSetAttribute(tc_bwd_kernel<SIM, UNI, MINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<SIM, UNI, MINE, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
   if (e != cudaSuccess) return e;
-  tc_bwd_kernel<SIM, UNI, MINE><<<ctas, NTHREADS, smem, st>>>(tmJ, z, a);
+  tc_bwd_kernel<SIM, UNI, MINE, NCH><<<ctas, tc_threads(NCH), smem, st>>>(tmJ, z, a);
   return cudaGetLastError();
 }
 template <int SIM, bool UNI>
 static cudaError_t launch_bwd_m(bool mine, const CUtensorMap& tmJ, const __nv_bfloat16* z, const TcBwdArgs& a, int ctas,
                                 size_t smem, cudaStream_t st) {
-  return mine ? launch_bwd<SIM, UNI, true>(tmJ, z, a, ctas, smem, st) : launch_bwd<SIM, UNI, false>(tmJ, z, a, ctas, smem, st);
+  const int nch = knobs().bwd_nch == 1 || knobs().bwd_nch == 2 ? knobs().bwd_nch
+                                                                : (mine ? BWD_MINE_NCH_DEFAULT : BWD_NCH_DEFAULT);
+  if (nch == 2)
+    return mine ? launch_bwd<SIM, UNI, true, 2>(tmJ, z, a, ctas, smem, st)
+                : launch_bwd<SIM, UNI, false, 2>(tmJ, z, a, ctas, smem, st);
+  return mine ? launch_bwd<SIM, UNI, true, 1>(tmJ, z, a, ctas, smem, st)
+              : launch_bwd<SIM, UNI, false, 1>(tmJ, z, a, ctas, smem, st);
 }
 
 int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, const float* stats,
