@@ -419,11 +419,12 @@ def main():
                   **extra_kw)
     loss_fn.kernel_flags = args.flags
     loss_fn.assume_unit_rows = True
-    # kernels of libsupcon_b200.so per step on the tensor path.  One GPU: prep_fwd, label_table, tc_fwd, merge,
+    # kernels of libsupcon_b200.so per step on the tensor path.  One GPU: prep_fwd, label_table, class_sum,
+    # class_reduce, tc_fwd (class-sum variant + its per-pair twin, one of which returns at once), merge,
     # prep_bwd, tc_bwd, reduce.  Several ranks: forward in two phases (prep + label_table + tc_fwd twice, merge),
     # finalize_sets, backward in two phases (prep_bwd + tc_bwd twice), reduce.
     # Peer exchange: push, forward in two phases (7), wait, push, wait, finalize_sets, backward (3), end_step = 16.
-    launches_per_step = 7 if world == 1 else 14
+    launches_per_step = 10 if world == 1 else 14
     launches = {"count": 0}
 
     def step(z_loc, y_loc):

@@ -419,3 +419,34 @@ def test_backward_column_panels_beyond_l2(cuda_device):
     prob2 = _tc_problem(n, tau=tau, topk=15, alpha=0.0, row_offset=r0 - 2048, n_rows=nl)
     dz2 = Fn.backward_rows(zz, yy, stats_all, partials, None, prob2, out_dtype=torch.float32)
     assert G.rel_err(dz2[2048:].cpu(), dz[:nl - 2048].cpu()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# positives by linearity (round 2): sum over positives from class sums for <= 32 classes, per pair beyond
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("classes", [1, 2, 5, 32, 33, 100])
+@pytest.mark.parametrize("lam", [0.0, 0.05])
+def test_tensor_path_positive_sums_for_any_class_count(cuda_device, classes, lam):
+    """cosine, no mining, whole forward on the tensor path: loss, row statistics (pos_mean) and dz against the
+    oracle whether the positives' sum comes from the class sums (<= TC_CMAX = 32 classes) or from the sweep."""
+    n, tau = 1000, 0.07                     # ragged: 8 row blocks, the last one partial
+    x, _ = O.make_inputs(n, 256, "iso", seed=5)
+    g = torch.Generator().manual_seed(classes)
+    y = torch.randint(0, classes, (n,), generator=g) * 7 - 3           # arbitrary label values
+    zb = F.normalize(x, dim=1).to(torch.bfloat16)
+    want = G.oracle_for(zb.double(), y, tau=tau, similarity="cosine", lam=lam, topk=15, alpha=0.0)
+    loss, dz = G.kernel_loss_and_grad(zb, y, tau=tau, similarity="cosine", lam=lam, topk=15, alpha=0.0,
+                                      dtype=torch.bfloat16, device=cuda_device, unit_rows=True)
+    assert loss == pytest.approx(want["loss"], rel=TOL_BF16)
+    assert G.rel_err(dz, want["dz"]) < TOL_BF16 or float(want["dz"].norm()) < 1e-9
+    # row statistics straight from the C-ABI: mean positive logit of every row
+    zz = Fn.canonical_z(zb.to(cuda_device))
+    yy = Fn.canonical_labels(y.to(cuda_device), n)
+    prob = _tc_problem(n, tau=tau, topk=15, alpha=0.0, lam=lam)
+    stats, _, _ = Fn.forward_rows(zz, yy, prob, want_loss=True)
+    s64 = zb.double() @ zb.double().T
+    same = (y[:, None] == y[None, :]) & ~torch.eye(n, dtype=torch.bool)
+    npos = same.sum(1)
+    pmean = torch.where(npos > 0, (s64 * same).sum(1) / tau / npos.clamp(min=1), torch.zeros(n, dtype=torch.float64))
+    assert torch.equal(stats.view(torch.int32)[:, _cabi.ST_NPOS].long().cpu(), npos)
+    assert float((stats[:, _cabi.ST_POS_MEAN].double().cpu() - pmean).abs().max()) < 2e-4

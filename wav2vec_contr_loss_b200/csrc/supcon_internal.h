@@ -66,8 +66,11 @@ struct TcPlan {
   int bwd_spp;                                 // backward: partial-record slots per column panel
   size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
       off_scalars, off_hkeys, off_hcounts, off_topk_v, off_topk_i, off_part, total_bytes;
+  size_t off_hids, off_csum_part, off_csum;   // positives by linearity: class ids, per-block and total class sums
+  int csum_blocks;                            // blocks of tc_class_sum_kernel (256 columns each)
   uint32_t hash_size;
 };
+constexpr int TC_CMAX = 32;         // most classes the class-sum route handles (more: per-pair sums in the sweep)
 constexpr int TC_MAX_PASSES = 4;    // passes of a multi-pass forward (own columns + up to three groups of peers)
 constexpr int TC_MAX_BLOCKS = 16;   // rank blocks one pass may list
 struct TcBlockList {                // column blocks a launch sweeps, in sweep order: block b covers `len` units from start[b]
@@ -81,6 +84,14 @@ struct TcFwdArgs {
   const int* hcounts;
   uint32_t hmask;
   const unsigned* nrm2_max;          // bits of max_j |z_j|^2 over the columns swept so far (workspace header)
+  // positives by linearity (cosine, no mining, whole forward): sum_{j in pos(i)} z_i.z_j = z_i . C[class_i] - |z_i|^2
+  // with C[c] = sum of the rows of class c.  n_classes == nullptr: off.  plin_twin: this launch is the per-pair
+  // kernel that only runs when there are more than TC_CMAX classes (its twin returns at once in that case).
+  const int* n_classes;              // distinct labels seen by the label table (workspace header)
+  const int* hids;                   // dense class id of every table slot
+  const float* csum;                 // [TC_CMAX][256] class sums
+  const void* z_rows;                // z (bf16), read by the merge for the rows' dot products with the class sums
+  int plin_twin;
   float* part;       // [slots][rows_pad][8]
   float* topk_v;     // [splits][rows_pad][kcap]  per-split hard-negative candidates (mining)
   int32_t* topk_i;

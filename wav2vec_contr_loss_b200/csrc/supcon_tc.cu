@@ -141,6 +141,7 @@ __device__ __forceinline__ int label_table_count(const unsigned long long* keys,
 // workspace header (first 256 bytes, zeroed by the forward's memset): word 0 = ticket of the merge kernel,
 // word 4 = bits of max_j |z_j|^2 over the columns swept so far (non-negative floats order like unsigned ints)
 constexpr int WS_NRM2_MAX_WORD = 4;
+constexpr int WS_NCLASSES_WORD = 5;   // number of distinct labels (positives by linearity)
 __device__ __forceinline__ float fixmax_from_bits(unsigned bits, float m_limit) {
   const float m2 = __uint_as_float(bits);
   if (m2 <= 1.015625f) return 1.0f;   // unit rows (bf16 rounding included): M == 1 exactly
@@ -202,9 +203,11 @@ __global__ void __launch_bounds__(256) tc_prep_fwd_kernel(const __nv_bfloat16* _
 
 // class sizes: one thread per column of [j_lo, n) minus the excluded window; lanes holding the same label are
 // aggregated (__match_any_sync) so a binary batch costs two atomics per warp instead of 32 on two addresses
+// hids / n_classes (optional): the thread that claims a slot also gives it the next dense class id
 __global__ void tc_label_table_kernel(const int32_t* __restrict__ labels, int n, unsigned long long* hkeys,
                                       int* hcounts, uint32_t hmask, int j_lo, int ex_lo, int ex_len,
-                                      TcBlockList bl = TcBlockList{0, 1, {0}}) {
+                                      TcBlockList bl = TcBlockList{0, 1, {0}}, int* hids = nullptr,
+                                      int* n_classes = nullptr) {
   int j = j_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ex_lo) j += ex_len;
   if (bl.n > 0) {
@@ -221,10 +224,76 @@ __global__ void tc_label_table_kernel(const int32_t* __restrict__ labels, int n,
     uint32_t h = label_hash(lab, hmask);
     for (;;) {
       const unsigned long long prev = atomicCAS(&hkeys[h], 0ull, want);
+      if (prev == 0ull && hids != nullptr) hids[h] = atomicAdd(n_classes, 1);
       if (prev == 0ull || prev == want) { atomicAdd(&hcounts[h], __popc(peers)); break; }
       h = (h + 1) & hmask;
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// positives by linearity (cosine): sum_{j in pos(i)} s_ij = z_i . C[class(i)] - |z_i|^2 with C[c] = sum_{j in c} z_j,
+// O(N d) instead of a compare and a predicated add per PAIR in the sweep (2 of its 5.25 instructions per pair:
+// forward 1.55 -> 1.41 ms at N = 65536, profiles/r02_fwd_pos_by_linearity.md).  Deterministic: every block sums its
+// 256 columns in index order, the blocks are summed in block order.  Dense class ids come from the label table;
+// with more than TC_CMAX classes these kernels return at once and the sweep keeps its per-pair sums.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int label_table_id(const unsigned long long* keys, const int* ids, uint32_t mask,
+                                              int32_t lab) {
+  const unsigned long long want = (1ull << 32) | (unsigned long long)(uint32_t)lab;
+  uint32_t h = label_hash(lab, mask);
+  for (;;) {
+    const unsigned long long k = keys[h];
+    if (k == want) return ids[h];
+    if (k == 0ull) return -1;
+    h = (h + 1) & mask;
+  }
+}
+constexpr int CS_COLS = 128;   // columns per block of tc_class_sum_kernel
+__global__ void __launch_bounds__(256) tc_class_sum_kernel(const __nv_bfloat16* __restrict__ z,
+                                                           const int32_t* __restrict__ labels, int n,
+                                                           const unsigned long long* __restrict__ hkeys,
+                                                           const int* __restrict__ hids, uint32_t hmask,
+                                                           const int* __restrict__ n_classes,
+                                                           float* __restrict__ part) {
+  __shared__ float acc[TC_CMAX * TD];   // thread k owns element k of every class sum
+  __shared__ int ids_s[CS_COLS];
+  const int nc = *n_classes;
+  if (nc > TC_CMAX) return;
+  const int tid = threadIdx.x;
+  const int j0 = blockIdx.x * CS_COLS, cnt = min(CS_COLS, n - j0);
+  if (tid < CS_COLS) ids_s[tid] = tid < cnt ? label_table_id(hkeys, hids, hmask, labels[j0 + tid]) : 0;
+  for (int c = 0; c < nc; ++c) acc[c * TD + tid] = 0.f;
+  __syncthreads();
+  const __nv_bfloat16* zp = z + (int64_t)j0 * TD + tid;
+  int j = 0;
+  for (; j + 8 <= cnt; j += 8) {   // eight independent loads in flight, then the adds in column order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __bfloat162float(zp[(int64_t)(j + u) * TD]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[ids_s[j + u] * TD + tid] += v[u];
+  }
+  for (; j < cnt; ++j) acc[ids_s[j] * TD + tid] += __bfloat162float(zp[(int64_t)j * TD]);
+  for (int c = 0; c < nc; ++c) part[((int64_t)blockIdx.x * TC_CMAX + c) * TD + tid] = acc[c * TD + tid];
+}
+// block c sums class c over the blocks of tc_class_sum_kernel: four quarters of the block range in parallel, each in
+// block order, then the four in order (a fixed summation tree: deterministic)
+__global__ void __launch_bounds__(1024) tc_class_reduce_kernel(const float* __restrict__ part, int blocks,
+                                                               const int* __restrict__ n_classes,
+                                                               float* __restrict__ csum) {
+  __shared__ float q[4][TD];
+  const int nc = *n_classes, c = blockIdx.x;
+  if (nc > TC_CMAX || c >= nc) return;
+  const int k = threadIdx.x & (TD - 1), seg = threadIdx.x >> 8;
+  const int per = (blocks + 3) / 4, b0 = seg * per, b1 = min(blocks, b0 + per);
+  float s = 0.f;
+  const float* p = part + (int64_t)c * TD + k;
+#pragma unroll 8
+  for (int b = b0; b < b1; ++b) s += p[(int64_t)b * TC_CMAX * TD];
+  q[seg][k] = s;
+  __syncthreads();
+  if (seg == 0) csum[c * TD + k] = ((q[0][k] + q[1][k]) + q[2][k]) + q[3][k];
 }
 
 // column coefficient vectors of H (SURVEY Appendix A with the fixed maximum 1/tau):
@@ -362,7 +431,7 @@ __device__ __noinline__ MineState mine_candidates(int sim, uint32_t taddr_chunk,
   return ms;
 }
 
-template <int SIM, bool UNI, bool MINE, bool MASKED, int POLY>
+template <int SIM, bool UNI, bool MINE, bool MASKED, int POLY, bool PLIN>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int gi, int n_total, int lab_r,
                                           float nrm_r, const int32_t* __restrict__ lab_s,
                                           const float* __restrict__ nrm_s, float c1, float c0, float ut2,
@@ -382,7 +451,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
       const float c = __uint_as_float(r[4 * q + e]);
       const float s = (SIM == SUPCON_GEODESIC) ? geodesic_sim_fast(c) : c;
       float ex = poly_elem<POLY>(4 * q + e) ? ex2_poly(fmaf(s, c1, c0)) : ex2f(fmaf(s, c1, c0));
-      bool pos = labs[e] == lab_r;
+      bool pos = PLIN ? false : labs[e] == lab_r;   // PLIN: the positives' sum comes from the class sums (merge)
       bool neg = !pos;
       if (MASKED) {
         const int gj = gj0 + 4 * q + e;
@@ -447,10 +516,14 @@ __device__ __forceinline__ void load_rows_to_tmem(const __nv_bfloat16* __restric
 // releases the TMEM buffer at once (the next MMA into it overlaps the exp work) and then reduces
 // from registers.  All pipeline barriers are indexed by a running tile counter, so segments
 // follow each other without draining the TMA ring.
-template <int SIM, bool UNI, bool MINE, int POLY, int NCH>
+template <int SIM, bool UNI, bool MINE, int POLY, int NCH, bool PLIN>
 __global__ void __launch_bounds__(tc_threads(NCH), 1) tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                     const __nv_bfloat16* __restrict__ z, TcFwdArgs a) {
   static_assert(NCH == 1 || (NCH == 2 && !MINE), "the top-K lists are kept by one thread per row");
+  static_assert(!PLIN || (SIM == SUPCON_COSINE && !MINE), "positives by linearity: cosine, no per-pair positive terms");
+  // positives by linearity: this kernel and its per-pair twin are both launched, the class count picks one
+  if (PLIN && *a.n_classes > TC_CMAX) return;
+  if (!PLIN && a.plin_twin && *a.n_classes <= TC_CMAX) return;
   constexpr int BN = 128;
   constexpr int CW = BN / NCH;                       // tile columns per thread
   constexpr uint32_t BOX_BYTES = 128 * 128;          // 128 rows x 128 B
@@ -597,18 +670,18 @@ __global__ void __launch_bounds__(tc_threads(NCH), 1) tc_fwd_kernel(const __grid
         const int32_t* lab_s = lab_ring[slot] + cc;
         const float* nrm_s = nrm_ring[UNI ? slot : 0] + cc;
         if (masked) {
-          fwd_chunk<SIM, UNI, MINE, true, POLY>(r0, col0 + cc, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
-          fwd_chunk<SIM, UNI, MINE, true, POLY>(r1, col0 + cc + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
+          fwd_chunk<SIM, UNI, MINE, true, POLY, PLIN>(r0, col0 + cc, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
+          fwd_chunk<SIM, UNI, MINE, true, POLY, PLIN>(r1, col0 + cc + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
           if constexpr (NCH == 1) {
-            fwd_chunk<SIM, UNI, MINE, true, POLY>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
-            fwd_chunk<SIM, UNI, MINE, true, POLY>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+            fwd_chunk<SIM, UNI, MINE, true, POLY, PLIN>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
+            fwd_chunk<SIM, UNI, MINE, true, POLY, PLIN>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
           }
         } else {
-          fwd_chunk<SIM, UNI, MINE, false, POLY>(r0, col0 + cc, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
-          fwd_chunk<SIM, UNI, MINE, false, POLY>(r1, col0 + cc + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
+          fwd_chunk<SIM, UNI, MINE, false, POLY, PLIN>(r0, col0 + cc, gi, a.n_total, lab_r, nrm_r, lab_s, nrm_s, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr);
+          fwd_chunk<SIM, UNI, MINE, false, POLY, PLIN>(r1, col0 + cc + 32, gi, a.n_total, lab_r, nrm_r, lab_s + 32, nrm_s + 32, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 32);
           if constexpr (NCH == 1) {
-            fwd_chunk<SIM, UNI, MINE, false, POLY>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
-            fwd_chunk<SIM, UNI, MINE, false, POLY>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
+            fwd_chunk<SIM, UNI, MINE, false, POLY, PLIN>(r2, col0 + 64, gi, a.n_total, lab_r, nrm_r, lab_s + 64, nrm_s + 64, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 64);
+            fwd_chunk<SIM, UNI, MINE, false, POLY, PLIN>(r3, col0 + 96, gi, a.n_total, lab_r, nrm_r, lab_s + 96, nrm_s + 96, a.c1, c0, a.ut2, st, ms, wl_v, wl_i, lane, K, taddr + 96);
           }
         }
         if (MINE) {   // candidates re-read S from tensor memory: release the buffer only now
@@ -653,8 +726,37 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
   __shared__ double red[7 * 128];
   __shared__ float mrg_v[TC_KCAP * 128];   // per-thread merge lists, entry-major (conflict-free)
   __shared__ int mrg_i[TC_KCAP * 128];
+  __shared__ int cls_s[128];       // positives by linearity: class id and z_i . C[class_i] of the block's rows
+  __shared__ float posdot_s[128];
   const int lr = blockIdx.x * 128 + threadIdx.x;
   double l_full = 0.0, c_full = 0.0, l_mined = 0.0, c_mined = 0.0, w = 0.0;
+  const bool plin = a.n_classes != nullptr && *a.n_classes <= TC_CMAX;
+  if (plin) {
+    cls_s[threadIdx.x] = lr < a.n_rows ? label_table_id(a.hkeys, a.hids, a.hmask, a.lab_pad[a.row_offset + lr]) : -1;
+    __syncthreads();
+    // one warp per row, four rows in flight per warp: 8 elements per lane
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = wib; r < 128; r += 4) {
+      const int c = cls_s[r];
+      float dot = 0.f;
+      if (c >= 0) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.z_rows) +
+                                                             (int64_t)(a.row_offset + blockIdx.x * 128 + r) * TD) + lane);
+        const float4 c0v = *reinterpret_cast<const float4*>(a.csum + c * TD + 8 * lane);
+        const float4 c1v = *reinterpret_cast<const float4*>(a.csum + c * TD + 8 * lane + 4);
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        const float cs[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[q]));
+          dot = fmaf(f.x, cs[2 * q], dot); dot = fmaf(f.y, cs[2 * q + 1], dot);
+        }
+      }
+      dot = warp_sum(dot);
+      if (lane == 0) posdot_s[r] = dot;
+    }
+    __syncthreads();
+  }
   // final fixed maximum (all columns seen): records of an earlier phase may carry a smaller one and are rescaled
   const float M = fixmax_from_bits(*a.nrm2_max, a.m_limit);
   const float c0 = -a.c1 * M, m_tau = M * a.inv_tau;
@@ -683,6 +785,7 @@ __global__ void __launch_bounds__(128) tc_fwd_merge_kernel(TcFwdArgs a, FinishAr
         sum_all = fmaf(v.x, scale, sum_all); sum_pos_s += v.y; wsum += v.z;
         sum_pos_e = fmaf(rec[4], scale, sum_pos_e);
       }
+    if (plin) sum_pos_s = posdot_s[threadIdx.x] - a.nrm_pad[a.row_offset + lr];   // minus the self term z_i . z_i
     const int nneg = a.n_total - 1 - npos;
     const float lse = logf(sum_all) + m_tau;   // fixed maximum M/tau folded back in
     const float pos_mean = npos > 0 ? (sum_pos_s * a.inv_tau) / (float)npos : 0.f;
@@ -1142,6 +1245,7 @@ struct TcKnobs {
   int fwd_ctas, bwd_ctas, local_ctas, local_free_sms, bwd_local_free_sms, bwd_panels;
   int fwd_poly;   // 4: a quarter of the forward's exponentials evaluated off the MUFU unit (A/B only); else none
   int fwd_nch, bwd_nch;   // threads per tile row (1 or 2; 0 = built-in choice), see tc_threads()
+  int fwd_plin;           // positives by linearity in the whole-batch cosine forward: 0 = off, else on
 };
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -1152,7 +1256,7 @@ const TcKnobs& knobs() {
                             env_int("SUPCON_TC_LOCAL_CTAS", 0), env_int("SUPCON_TC_LOCAL_FREE_SMS", 32),
                             env_int("SUPCON_TC_BWD_LOCAL_FREE_SMS", 16), env_int("SUPCON_TC_BWD_PANELS", 0),
                             env_int("SUPCON_TC_FWD_POLY", -1), env_int("SUPCON_TC_FWD_NCH", 0),
-                            env_int("SUPCON_TC_BWD_NCH", 0)};
+                            env_int("SUPCON_TC_BWD_NCH", 0), env_int("SUPCON_TC_FWD_PLIN", 1)};
   return k;
 }
 
@@ -1308,6 +1412,10 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.hash_size = hsize;
   pl.off_hkeys = off; off += (size_t)hsize * 8;      // keys then counts: one memset clears both
   pl.off_hcounts = off; off += (size_t)hsize * 4;
+  pl.off_hids = off; off += (size_t)hsize * 4;
+  pl.csum_blocks = (p->n_total + 127) / 128;   // CS_COLS columns per block
+  pl.off_csum = off; off += (size_t)TC_CMAX * TD * sizeof(float);
+  pl.off_csum_part = off; off += align_up((size_t)pl.csum_blocks * TC_CMAX * TD * sizeof(float), 256);
   const bool mine = p->alpha != 0.f && p->topk >= 1;
   const size_t kcap = mine ? (size_t)(p->topk < TC_KCAP ? p->topk : TC_KCAP) : 0;
   pl.off_topk_v = off; off += align_up((size_t)pl.fwd_slots * pl.rows_pad * kcap * 4, 256);
@@ -1360,13 +1468,13 @@ constexpr int FWD_POLY_DEFAULT = 0;
 // (1.663 -> 1.595 ms), the mined backward 13 % (6.93 -> 6.01 ms: its membership tests make it issue-bound and more
 // warps fill the slots); the unmined backward gets SLOWER and unsteady with two (3.11 -> 3.36-3.51 ms median).
 constexpr int FWD_NCH_DEFAULT = 2, BWD_NCH_DEFAULT = 1, BWD_MINE_NCH_DEFAULT = 2;
-template <int SIM, bool UNI, bool MINE, int POLY, int NCH>
+template <int SIM, bool UNI, bool MINE, int POLY, int NCH, bool PLIN = false>
 static cudaError_t launch_fwd(const CUtensorMap& tm, const __nv_bfloat16* z, const TcFwdArgs& a, int ctas, size_t smem,
                               cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<SIM, UNI, MINE, POLY, NCH>,
+  cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<SIM, UNI, MINE, POLY, NCH, PLIN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_fwd_kernel<SIM, UNI, MINE, POLY, NCH><<<ctas, tc_threads(NCH), smem, st>>>(tm, z, a);
+  tc_fwd_kernel<SIM, UNI, MINE, POLY, NCH, PLIN><<<ctas, tc_threads(NCH), smem, st>>>(tm, z, a);
   return cudaGetLastError();
 }
 template <int SIM, bool UNI>
@@ -1377,6 +1485,16 @@ static cudaError_t launch_fwd_m(bool mine, const CUtensorMap& tm, const __nv_bfl
   if (mine) return launch_fwd<SIM, UNI, true, 0, 1>(tm, z, a, ctas, smem, st);
   const int poly = knobs().fwd_poly < 0 ? FWD_POLY_DEFAULT : knobs().fwd_poly;
   const int nch = knobs().fwd_nch == 1 || knobs().fwd_nch == 2 ? knobs().fwd_nch : FWD_NCH_DEFAULT;
+  // positives by linearity (the caller set it up: cosine only): the class-sum kernel first, then its per-pair twin;
+  // exactly one of the two does the sweep, decided on the device by the class count
+  if (SIM == SUPCON_COSINE && a.n_classes != nullptr) {
+    cudaError_t e = launch_fwd<SUPCON_COSINE, UNI, false, 0, 2, true>(tm, z, a, ctas, smem, st);
+    if (e != cudaSuccess) return e;
+    TcFwdArgs b = a;
+    b.plin_twin = 1;
+    if (nch == 2) return launch_fwd<SUPCON_COSINE, UNI, false, 0, 2>(tm, z, b, ctas, smem, st);
+    return launch_fwd<SUPCON_COSINE, UNI, false, 0, 1>(tm, z, b, ctas, smem, st);
+  }
   // the polynomial share exists for the headline variant only (A/B measurement: profiles/r02_fwd_poly_ab.md)
   if (SIM == SUPCON_COSINE && !UNI && poly == 4) {
     if (nch == 2) return launch_fwd<SUPCON_COSINE, false, false, 4, 2>(tm, z, a, ctas, smem, st);
@@ -1400,6 +1518,7 @@ static TcFwdArgs fwd_base_args(const supcon_problem_t* p, const TcPlan& pl, char
   a.hcounts = reinterpret_cast<const int*>(ws + pl.off_hcounts);
   a.hmask = pl.hash_size - 1;
   a.nrm2_max = reinterpret_cast<unsigned*>(ws) + WS_NRM2_MAX_WORD;
+  a.n_classes = nullptr; a.hids = nullptr; a.csum = nullptr; a.z_rows = nullptr; a.plin_twin = 0;
   a.ct_base = 0; a.ex_lo = 0x7fffffff; a.ex_len = 0; a.slot_base = 0;
   a.blocks.n = 0; a.blocks.len = 1;
   a.npass = 0;
@@ -1466,12 +1585,33 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
     int jn_lo = j_lo, jn_ex_lo = ex_lo, jn_ex_len = ex_len, jn_count = p->n_total;
     if (phase == 1) { jn_count = p->n_rows; jn_ex_lo = jn_lo + jn_count; jn_ex_len = p->n_total; }
     if (phase == 2) { jn_count = p->n_total - p->n_rows; jn_ex_len = p->n_rows; }
+    // positives by linearity: whole forward (one phase), cosine, no mining
+    const bool plin = phase == 0 && p->similarity == SUPCON_COSINE && !(p->alpha != 0.f && p->topk >= 1) &&
+                      knobs().fwd_plin != 0;
+    int* n_classes = reinterpret_cast<int*>(ws) + WS_NCLASSES_WORD;
+    int* hids = reinterpret_cast<int*>(ws + pl.off_hids);
     if (jn_count > 0)
       tc_label_table_kernel<<<(jn_count + 255) / 256, 256, 0, stream>>>(
           labels_all, p->n_total, reinterpret_cast<unsigned long long*>(ws + pl.off_hkeys),
-          reinterpret_cast<int*>(ws + pl.off_hcounts), pl.hash_size - 1, jn_lo, jn_ex_lo, jn_ex_len);
+          reinterpret_cast<int*>(ws + pl.off_hcounts), pl.hash_size - 1, jn_lo, jn_ex_lo, jn_ex_len,
+          TcBlockList{0, 1, {0}}, plin ? hids : nullptr, plin ? n_classes : nullptr);
+    if (plin) {
+      tc_class_sum_kernel<<<pl.csum_blocks, 256, 0, stream>>>(
+          reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all, p->n_total,
+          reinterpret_cast<const unsigned long long*>(ws + pl.off_hkeys), hids, pl.hash_size - 1, n_classes,
+          reinterpret_cast<float*>(ws + pl.off_csum_part));
+      tc_class_reduce_kernel<<<TC_CMAX, 1024, 0, stream>>>(reinterpret_cast<const float*>(ws + pl.off_csum_part),
+                                                         pl.csum_blocks, n_classes,
+                                                         reinterpret_cast<float*>(ws + pl.off_csum));
+    }
   }
   TcFwdArgs a = fwd_base_args(p, pl, ws);
+  if (phase == 0 && p->similarity == SUPCON_COSINE && !(p->alpha != 0.f && p->topk >= 1) && knobs().fwd_plin != 0) {
+    a.n_classes = reinterpret_cast<const int*>(ws) + WS_NCLASSES_WORD;
+    a.hids = reinterpret_cast<const int*>(ws + pl.off_hids);
+    a.csum = reinterpret_cast<const float*>(ws + pl.off_csum);
+    a.z_rows = z_all;
+  }
   if (phase == 1) { a.sched = pl.fwd_sched_local; a.ct_base = pl.local_ct0; }
   if (phase == 2) { a.sched = pl.fwd_sched_remote; a.ex_lo = pl.local_ct0; a.ex_len = pl.local_cts; a.slot_base = pl.slots_local; }
   e = fwd_launch_kernel(p, tm, z_all, a, stream);
