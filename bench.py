@@ -424,7 +424,10 @@ def main():
     # prep_bwd, tc_bwd, reduce.  Several ranks: forward in two phases (prep + label_table + tc_fwd twice, merge),
     # finalize_sets, backward in two phases (prep_bwd + tc_bwd twice), reduce.
     # Peer exchange: push, forward in two phases (7), wait, push, wait, finalize_sets, backward (3), end_step = 16.
-    launches_per_step = 10 if world == 1 else 14
+    # The single-phase backward of >= 2^30 pairs adds label_table, class_sum, class_reduce and its own twin.
+    class_sums = args.similarity == "cosine" and args.alpha == 0.0
+    bwd_extra = 4 if (class_sums and n_local * n >= (1 << 30)) else 0
+    launches_per_step = (7 + (3 if class_sums else 0) + bwd_extra) if world == 1 else 14
     launches = {"count": 0}
 
     def step(z_loc, y_loc):
@@ -475,7 +478,7 @@ def main():
     if world > 1:
         exchange_used = "peer" if any(v is not None for v in loss_fn._peers.values()) else "nccl"
         if exchange_used == "peer":
-            launches_per_step = 16
+            launches_per_step = 16 + bwd_extra
 
     # ---- host-inclusive time of the same call issued eagerly from Python (both figures) ----
     def eager_ms(fn, reps):

@@ -133,6 +133,15 @@ struct TcBwdArgs {
   int spp;               // partial-record slots per panel of `sched`
   int n_total, n_pad, row_offset, n_rows, rows_pad;
   float c1, c0, ut2;
+  // positives by linearity (cosine, no mining, single-phase backward): B is constant within a class, so
+  // -sum_{j in pos(i)} (B_i + B_j) z_j = -2 B_i (C[class_i] - z_i) is added in fp32 by the reduce kernel and the
+  // sweep forms H without the per-pair label compare.  n_classes == nullptr: off; plin_twin as in TcFwdArgs.
+  const int* n_classes;
+  const unsigned long long* hkeys;
+  const int* hids;
+  uint32_t hmask;
+  const float* csum;     // [TC_CMAX][256]
+  int plin_twin;
 };
 TcPlan tc_plan(const supcon_problem_t* p);
 bool tc_supported(const supcon_problem_t* p);

@@ -875,7 +875,7 @@ struct RowMine {  // the same for this thread's row
   int thr_idx;
 };
 
-template <int SIM, bool UNI, bool MINE, bool MASKED, int NQ>
+template <int SIM, bool UNI, bool MINE, bool MASKED, int NQ, bool PLIN>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[4 * NQ], uint32_t (&hw)[2 * NQ], int gj0, int gi, int lab_r,
                                           float A_r, float B_r, float nrm_r, float cu, float c0, const ColVecs& cv,
                                           const RowMine& rm, const TcBwdArgs& a) {
@@ -915,7 +915,7 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[4 * NQ], uint32_t 
         const bool mem_c = pos | (s > Ts[e]) | ((s == Ts[e]) & (gi <= Is[e]));
         v = fmaf(e0, (mem_r ? rm.Am : 0.f) + (mem_c ? Ams[e] : 0.f), v);
       }
-      if (labs[e] == lab_r) v -= B_r + Bs[e];
+      if (!PLIN && labs[e] == lab_r) v -= B_r + Bs[e];   // PLIN: the reduce kernel adds the positives' term
       if (SIM == SUPCON_GEODESIC) v *= geodesic_slope_fast(c);
       if (UNI) v = fmaf(-cu, ex2f(-a.ut2 * fmaxf(nrm_r + njs[e] - 2.f * c, 0.f)), v);
       if (MASKED) v = (gj0 + 4 * q + e == gi) ? 0.f : v;
@@ -953,10 +953,14 @@ __device__ __forceinline__ int bwd_col_tile(const TcBwdArgs& a, int ct) {
 // what holds the pipe at ~75 %.  What the variants share is the shared-memory traffic per tile: 32 KB read by
 // the S MMAs + 32 KB by the dZ MMAs + 32 KB written by TMA = 94 B/clk of the 128 B/clk port; sharing Z_J
 // between two CTAs (cta_group::2) is the remaining lever.
-template <int SIM, bool UNI, bool MINE, int NCH>
+template <int SIM, bool UNI, bool MINE, int NCH, bool PLIN>
 __global__ void __launch_bounds__(tc_threads(NCH), 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapJ,
                                                                     const __nv_bfloat16* __restrict__ z, TcBwdArgs a) {
   static_assert(NCH == 1 || NCH == 2, "one or two threads per tile row");
+  static_assert(!PLIN || (SIM == SUPCON_COSINE && !MINE), "positives by linearity: cosine, no mining");
+  // positives by linearity: this kernel and its per-pair twin are both launched, the class count picks one
+  if (PLIN && *a.n_classes > TC_CMAX) return;
+  if (!PLIN && a.plin_twin && *a.n_classes <= TC_CMAX) return;
   constexpr int BN = 64;
   constexpr int CW = BN / NCH;                         // tile columns per thread
   constexpr int STAGES = 6;
@@ -1140,16 +1144,16 @@ __global__ void __launch_bounds__(tc_threads(NCH), 1) tc_bwd_kernel(const __grid
         cv1.Am = cv0.Am + 32; cv1.thr = cv0.thr + 32; cv1.thr_idx = cv0.thr_idx + 32;
         const bool masked = (col0 < row0 + TBM && row0 < col0 + BN);
         if (masked) {
-          bwd_chunk<SIM, UNI, MINE, true, 8>(r0, h0, col0 + cc, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv0, rm, a);
+          bwd_chunk<SIM, UNI, MINE, true, 8, PLIN>(r0, h0, col0 + cc, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv0, rm, a);
         } else {
-          bwd_chunk<SIM, UNI, MINE, false, 8>(r0, h0, col0 + cc, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv0, rm, a);
+          bwd_chunk<SIM, UNI, MINE, false, 8, PLIN>(r0, h0, col0 + cc, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv0, rm, a);
         }
         if constexpr (NCH == 1) {
           uint32_t (&h1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&hw[16]);
           if (masked) {
-            bwd_chunk<SIM, UNI, MINE, true, 8>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv1, rm, a);
+            bwd_chunk<SIM, UNI, MINE, true, 8, PLIN>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv1, rm, a);
           } else {
-            bwd_chunk<SIM, UNI, MINE, false, 8>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv1, rm, a);
+            bwd_chunk<SIM, UNI, MINE, false, 8, PLIN>(r1, h1, col0 + 32, gi, lab_r, A_r, B_r, nrm_r, cu, c0, cv1, rm, a);
           }
           ptx::tmem_st32(sbuf, hw);          // H(t): 64 bf16 = 32 packed columns over S(t)
         } else {
@@ -1220,6 +1224,18 @@ __global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const _
     }
   }
   const int gi = a.row_offset + lr;
+  if (a.n_classes != nullptr && *a.n_classes <= TC_CMAX) {
+    // positives by linearity: - sum_{j in pos(i)} (B_i + B_j) z_j = -2 B_i (C[class_i] - z_i), in fp32
+    const float Bi = a.colB[gi];
+    if (Bi != 0.f) {
+      const int c = label_table_id(a.hkeys, a.hids, a.hmask, a.lab_pad[gi]);
+      const float4 cs = *reinterpret_cast<const float4*>(a.csum + c * TD + 4 * c4);
+      const __nv_bfloat16* zr = z + (int64_t)gi * TD + 4 * c4;
+      const float m = -2.f * Bi;
+      acc.x = fmaf(m, cs.x - __bfloat162float(zr[0]), acc.x); acc.y = fmaf(m, cs.y - __bfloat162float(zr[1]), acc.y);
+      acc.z = fmaf(m, cs.z - __bfloat162float(zr[2]), acc.z); acc.w = fmaf(m, cs.w - __bfloat162float(zr[3]), acc.w);
+    }
+  }
   const float cu = a.scalars[0];
   if (cu != 0.f) {
     const float wd = cu * stats_all[(int64_t)gi * SUPCON_STATS_STRIDE + SUPCON_ST_WSUM];
@@ -1245,7 +1261,7 @@ struct TcKnobs {
   int fwd_ctas, bwd_ctas, local_ctas, local_free_sms, bwd_local_free_sms, bwd_panels;
   int fwd_poly;   // 4: a quarter of the forward's exponentials evaluated off the MUFU unit (A/B only); else none
   int fwd_nch, bwd_nch;   // threads per tile row (1 or 2; 0 = built-in choice), see tc_threads()
-  int fwd_plin;           // positives by linearity in the whole-batch cosine forward: 0 = off, else on
+  int fwd_plin, bwd_plin; // positives by linearity (cosine, no mining) in the forward / backward: 0 = off, else on
 };
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -1256,7 +1272,8 @@ const TcKnobs& knobs() {
                             env_int("SUPCON_TC_LOCAL_CTAS", 0), env_int("SUPCON_TC_LOCAL_FREE_SMS", 32),
                             env_int("SUPCON_TC_BWD_LOCAL_FREE_SMS", 16), env_int("SUPCON_TC_BWD_PANELS", 0),
                             env_int("SUPCON_TC_FWD_POLY", -1), env_int("SUPCON_TC_FWD_NCH", 0),
-                            env_int("SUPCON_TC_BWD_NCH", 0), env_int("SUPCON_TC_FWD_PLIN", 1)};
+                            env_int("SUPCON_TC_BWD_NCH", 0), env_int("SUPCON_TC_FWD_PLIN", 1),
+                            env_int("SUPCON_TC_BWD_PLIN", 1)};
   return k;
 }
 
@@ -1549,6 +1566,12 @@ static cudaError_t fwd_launch_kernel(const supcon_problem_t* p, const CUtensorMa
   return launch_fwd_m<SUPCON_COSINE, false>(mine, tm, zb, a, ctas, smem, stream);
 }
 
+// positives by linearity in the forward: whole forward (one phase), cosine, no mining
+static bool fwd_class_sums(const supcon_problem_t* p, int phase) {
+  return phase == 0 && p->similarity == SUPCON_COSINE && !(p->alpha != 0.f && p->topk >= 1) &&
+         knobs().fwd_plin != 0 && !(p->flags & SUPCON_FLAG_NO_CLASS_SUMS);
+}
+
 int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, float* row_stats,
                double* partials, float* loss_out, void* workspace, cudaStream_t stream, const char** err, int phase) {
   const TcPlan pl = tc_plan(p);
@@ -1586,8 +1609,7 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
     if (phase == 1) { jn_count = p->n_rows; jn_ex_lo = jn_lo + jn_count; jn_ex_len = p->n_total; }
     if (phase == 2) { jn_count = p->n_total - p->n_rows; jn_ex_len = p->n_rows; }
     // positives by linearity: whole forward (one phase), cosine, no mining
-    const bool plin = phase == 0 && p->similarity == SUPCON_COSINE && !(p->alpha != 0.f && p->topk >= 1) &&
-                      knobs().fwd_plin != 0;
+    const bool plin = fwd_class_sums(p, phase);
     int* n_classes = reinterpret_cast<int*>(ws) + WS_NCLASSES_WORD;
     int* hids = reinterpret_cast<int*>(ws + pl.off_hids);
     if (jn_count > 0)
@@ -1606,7 +1628,7 @@ int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labe
     }
   }
   TcFwdArgs a = fwd_base_args(p, pl, ws);
-  if (phase == 0 && p->similarity == SUPCON_COSINE && !(p->alpha != 0.f && p->topk >= 1) && knobs().fwd_plin != 0) {
+  if (fwd_class_sums(p, phase)) {
     a.n_classes = reinterpret_cast<const int*>(ws) + WS_NCLASSES_WORD;
     a.hids = reinterpret_cast<const int*>(ws + pl.off_hids);
     a.csum = reinterpret_cast<const float*>(ws + pl.off_csum);
@@ -1714,13 +1736,13 @@ int tc_forward_pass(const supcon_problem_t* p, const void* z_all, const int32_t*
   return 0;
 }
 
-template <int SIM, bool UNI, bool MINE, int NCH>
+template <int SIM, bool UNI, bool MINE, int NCH, bool PLIN = false>
 static cudaError_t launch_bwd(const CUtensorMap& tmJ, const __nv_bfloat16* z, const TcBwdArgs& a, int ctas, size_t smem,
                               cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<SIM, UNI, MINE, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<SIM, UNI, MINE, NCH, PLIN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_bwd_kernel<SIM, UNI, MINE, NCH><<<ctas, tc_threads(NCH), smem, st>>>(tmJ, z, a);
+  tc_bwd_kernel<SIM, UNI, MINE, NCH, PLIN><<<ctas, tc_threads(NCH), smem, st>>>(tmJ, z, a);
   return cudaGetLastError();
 }
 template <int SIM, bool UNI>
@@ -1728,6 +1750,15 @@ static cudaError_t launch_bwd_m(bool mine, const CUtensorMap& tmJ, const __nv_bf
                                 size_t smem, cudaStream_t st) {
   const int nch = knobs().bwd_nch == 1 || knobs().bwd_nch == 2 ? knobs().bwd_nch
                                                                 : (mine ? BWD_MINE_NCH_DEFAULT : BWD_NCH_DEFAULT);
+  // positives by linearity (the caller set it up: cosine, no mining): the class-sum kernel, then its per-pair twin
+  if (SIM == SUPCON_COSINE && !mine && a.n_classes != nullptr) {
+    cudaError_t e = launch_bwd<SUPCON_COSINE, UNI, false, 1, true>(tmJ, z, a, ctas, smem, st);
+    if (e != cudaSuccess) return e;
+    TcBwdArgs b = a;
+    b.plin_twin = 1;
+    if (nch == 2) return launch_bwd<SUPCON_COSINE, UNI, false, 2>(tmJ, z, b, ctas, smem, st);
+    return launch_bwd<SUPCON_COSINE, UNI, false, 1>(tmJ, z, b, ctas, smem, st);
+  }
   if (nch == 2)
     return mine ? launch_bwd<SIM, UNI, true, 2>(tmJ, z, a, ctas, smem, st)
                 : launch_bwd<SIM, UNI, false, 2>(tmJ, z, a, ctas, smem, st);
@@ -1757,6 +1788,30 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
                                                    reinterpret_cast<int32_t*>(ws + pl.off_lab),
                                                    reinterpret_cast<float*>(ws + pl.off_nrm),
                                                    reinterpret_cast<unsigned*>(ws + pl.off_scalars) + 8, pl.n_pad);
+  }
+  // positives by linearity: single-phase cosine backward without mining, when the sweep is long enough for its
+  // ~7 % to outweigh the ~30 us of class-sum kernels (a rank's share of at least 2^30 pairs)
+  const bool mine_b = p->alpha != 0.f && p->topk >= 1;
+  const bool plin = phase == 0 && p->similarity == SUPCON_COSINE && !mine_b && knobs().bwd_plin != 0 &&
+                    !(p->flags & SUPCON_FLAG_NO_CLASS_SUMS) &&
+                    ((long long)p->n_rows * p->n_total >= (1ll << 30) || (p->flags & SUPCON_FLAG_CLASS_SUMS));
+  int* n_classes = reinterpret_cast<int*>(ws) + WS_NCLASSES_WORD;
+  int* hids = reinterpret_cast<int*>(ws + pl.off_hids);
+  if (plin) {
+    e = cudaMemsetAsync(workspace, 0, 256, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws + pl.off_hkeys, 0, (size_t)pl.hash_size * 12, stream);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
+    tc_label_table_kernel<<<(p->n_total + 255) / 256, 256, 0, stream>>>(
+        labels_all, p->n_total, reinterpret_cast<unsigned long long*>(ws + pl.off_hkeys),
+        reinterpret_cast<int*>(ws + pl.off_hcounts), pl.hash_size - 1, 0, 0x7fffffff, 0, TcBlockList{0, 1, {0}}, hids,
+        n_classes);
+    tc_class_sum_kernel<<<pl.csum_blocks, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(z_all), labels_all, p->n_total,
+        reinterpret_cast<const unsigned long long*>(ws + pl.off_hkeys), hids, pl.hash_size - 1, n_classes,
+        reinterpret_cast<float*>(ws + pl.off_csum_part));
+    tc_class_reduce_kernel<<<TC_CMAX, 1024, 0, stream>>>(reinterpret_cast<const float*>(ws + pl.off_csum_part),
+                                                        pl.csum_blocks, n_classes,
+                                                        reinterpret_cast<float*>(ws + pl.off_csum));
   }
   TcBwdPrepArgs pa;
   pa.stats = stats; pa.partials = partials; pa.labels = labels_all;
@@ -1792,6 +1847,11 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   }
   a.c1 = LOG2E / p->tau; a.c0 = -a.c1; a.ut2 = p->uni_t * LOG2E;
   a.scalars = pa.scalars;
+  a.n_classes = plin ? n_classes : nullptr;
+  a.hkeys = reinterpret_cast<const unsigned long long*>(ws + pl.off_hkeys);
+  a.hids = hids; a.hmask = pl.hash_size - 1;
+  a.csum = reinterpret_cast<const float*>(ws + pl.off_csum);
+  a.plin_twin = 0;
   const size_t smem = 6 * (size_t)NBOX * 64 * 128 + 1024;   // 6 x 32 KB Z_J stages
   const int ctas = a.sched.P;
   const bool geo = p->similarity == SUPCON_GEODESIC;
