@@ -53,6 +53,33 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): two IEEE fp32 operations per issued instruction.  The hot loops
+// of the unmasked cosine tiles use them for the exponent argument, the running sum (even / odd columns in the two
+// halves) and the H coefficients: same arithmetic per element, fewer issue slots and half as long a dependent chain.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 // 2^x on the FMA / ALU pipes (no MUFU), for x in (-126, 127): Cody-Waite split x = n + f with n = floor(x) taken
 // from the low mantissa bits of x + 1.5 * 2^23 (rounded toward -inf), 2^f on [0, 1) by the degree-4 minimax
 // polynomial (relative error 2.7e-6, fp32 Horner included), 2^n added into the exponent field.  Built to take a
@@ -372,6 +399,7 @@ __host__ __device__ inline SchedRun sched_decode(const TcSched& s, long long u) 
 struct RowSums {
   float sum_all, sum_pos_s, wsum;
   float sum_pos_e;   // mining: sum of e over positives
+  f32x2 sum_all2;    // packed tiles: sums of e over the even / odd columns (added to sum_all at the end)
 };
 
 constexpr int TC_KCAP = 32;      // in-sweep list capacity per row on the tensor path
@@ -438,6 +466,35 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int gj0, int 
                                           RowSums& st, MineState& ms, float* wl_v, int* wl_i, int lane, int K,
                                           uint32_t taddr_chunk) {
   // lab_s / nrm_s: this chunk's 32 column labels / squared norms in shared memory (broadcast reads)
+  if constexpr (SIM == SUPCON_COSINE && !MINE && !MASKED && POLY == 0) {
+    // packed pairs: exponent arguments and the running sum, two columns per instruction
+    const f32x2 c1p = pk2(c1, c1), c0p = pk2(c0, c0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      int4 lb = make_int4(0, 0, 0, 0);
+      if (!PLIN) lb = *reinterpret_cast<const int4*>(lab_s + 4 * q);
+      float4 nj = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (UNI) nj = *reinterpret_cast<const float4*>(nrm_s + 4 * q);
+      const int labs[4] = {lb.x, lb.y, lb.z, lb.w};
+      const float njs[4] = {nj.x, nj.y, nj.z, nj.w};
+#pragma unroll
+      for (int e = 0; e < 4; e += 2) {
+        const float ca = __uint_as_float(r[4 * q + e]), cb = __uint_as_float(r[4 * q + e + 1]);
+        float xa, xb;
+        upk2(fma2(pk2(ca, cb), c1p, c0p), xa, xb);
+        st.sum_all2 = add2(st.sum_all2, pk2(ex2f(xa), ex2f(xb)));
+        if (!PLIN) {
+          if (labs[e] == lab_r) st.sum_pos_s += ca;
+          if (labs[e + 1] == lab_r) st.sum_pos_s += cb;
+        }
+        if (UNI) {
+          st.wsum += ex2f(-ut2 * fmaxf(nrm_r + njs[e] - 2.f * ca, 0.f));
+          st.wsum += ex2f(-ut2 * fmaxf(nrm_r + njs[e + 1] - 2.f * cb, 0.f));
+        }
+      }
+    }
+    return;
+  }
   unsigned cmask = 0;   // mining: elements of this chunk that beat the row's K-th value as of the chunk start
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -644,7 +701,7 @@ __global__ void __launch_bounds__(tc_threads(NCH), 1) tc_fwd_kernel(const __grid
       const int lab_r = a.lab_pad[min(gi, a.n_pad - 1)];
       const float nrm_r = UNI ? a.nrm_pad[min(gi, a.n_pad - 1)] : 0.f;
       RowSums st;
-      st.sum_all = 0.f; st.sum_pos_s = 0.f; st.wsum = 0.f; st.sum_pos_e = 0.f;
+      st.sum_all = 0.f; st.sum_pos_s = 0.f; st.wsum = 0.f; st.sum_pos_e = 0.f; st.sum_all2 = pk2(0.f, 0.f);
       MineState ms;
       ms.thr = -INFINITY; ms.cnt = 0;
       for (int t = 0; t < nt; ++t, ++g) {
@@ -688,6 +745,11 @@ __global__ void __launch_bounds__(tc_threads(NCH), 1) tc_fwd_kernel(const __grid
           ptx::tc_fence_before_sync();
           ptx::mbar_arrive(&bar_tempty[wg]);
         }
+      }
+      {
+        float even, odd;
+        upk2(st.sum_all2, even, odd);
+        st.sum_all += even + odd;
       }
       if constexpr (NCH == 2) {
         // the two threads of a row add their halves: the upper half goes through shared memory.  No second barrier
@@ -879,6 +941,48 @@ template <int SIM, bool UNI, bool MINE, bool MASKED, int NQ, bool PLIN>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[4 * NQ], uint32_t (&hw)[2 * NQ], int gj0, int gi, int lab_r,
                                           float A_r, float B_r, float nrm_r, float cu, float c0, const ColVecs& cv,
                                           const RowMine& rm, const TcBwdArgs& a) {
+  if constexpr (SIM == SUPCON_COSINE && !MINE && !MASKED) {
+    // packed pairs: exponent arguments, A_i + A_j and the product, two columns per instruction
+    const f32x2 c1p = pk2(a.c1, a.c1), c0p = pk2(c0, c0), Arp = pk2(A_r, A_r);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      int4 lb = make_int4(0, 0, 0, 0);
+      float4 Bj = make_float4(0.f, 0.f, 0.f, 0.f), nj = Bj;
+      if (!PLIN) {
+        lb = *reinterpret_cast<const int4*>(cv.lab + 4 * q);
+        Bj = *reinterpret_cast<const float4*>(cv.B + 4 * q);
+      }
+      const float4 Aj = *reinterpret_cast<const float4*>(cv.A + 4 * q);
+      if (UNI) nj = *reinterpret_cast<const float4*>(cv.nrm + 4 * q);
+      const int labs[4] = {lb.x, lb.y, lb.z, lb.w};
+      const float As[4] = {Aj.x, Aj.y, Aj.z, Aj.w};
+      const float Bs[4] = {Bj.x, Bj.y, Bj.z, Bj.w};
+      const float njs[4] = {nj.x, nj.y, nj.z, nj.w};
+      float h[4];
+#pragma unroll
+      for (int e = 0; e < 4; e += 2) {
+        const float ca = __uint_as_float(r[4 * q + e]), cb = __uint_as_float(r[4 * q + e + 1]);
+        float xa, xb;
+        upk2(fma2(pk2(ca, cb), c1p, c0p), xa, xb);
+        float va, vb;
+        upk2(mul2(pk2(ex2f(xa), ex2f(xb)), add2(Arp, pk2(As[e], As[e + 1]))), va, vb);
+        if (!PLIN) {
+          if (labs[e] == lab_r) va -= B_r + Bs[e];
+          if (labs[e + 1] == lab_r) vb -= B_r + Bs[e + 1];
+        }
+        if (UNI) {
+          va = fmaf(-cu, ex2f(-a.ut2 * fmaxf(nrm_r + njs[e] - 2.f * ca, 0.f)), va);
+          vb = fmaf(-cu, ex2f(-a.ut2 * fmaxf(nrm_r + njs[e + 1] - 2.f * cb, 0.f)), vb);
+        }
+        h[e] = va; h[e + 1] = vb;
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(h[0], h[1]);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(h[2], h[3]);
+      hw[2 * q] = *reinterpret_cast<uint32_t*>(&p0);
+      hw[2 * q + 1] = *reinterpret_cast<uint32_t*>(&p1);
+    }
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int4 lb = *reinterpret_cast<const int4*>(cv.lab + 4 * q);
