@@ -425,9 +425,11 @@ def main():
     # finalize_sets, backward in two phases (prep_bwd + tc_bwd twice), reduce.
     # Peer exchange: push, forward in two phases (7), wait, push, wait, finalize_sets, backward (3), end_step = 16.
     # The single-phase backward of >= 2^30 pairs adds label_table, class_sum, class_reduce and its own twin.
+    # (one GPU: the module hands the forward's workspace to the backward, which then only adds its twin.)
     class_sums = args.similarity == "cosine" and args.alpha == 0.0
-    bwd_extra = 4 if (class_sums and n_local * n >= (1 << 30)) else 0
-    launches_per_step = (7 + (3 if class_sums else 0) + bwd_extra) if world == 1 else 14
+    bwd_plin = class_sums and n_local * n >= (1 << 30)
+    bwd_extra = 4 if bwd_plin else 0
+    launches_per_step = (7 + (3 if class_sums else 0) + (1 if bwd_plin else 0)) if world == 1 else 14
     launches = {"count": 0}
 
     def step(z_loc, y_loc):

@@ -67,6 +67,7 @@ struct TcPlan {
   size_t off_block_partials, off_lab, off_nrm, off_colA, off_colAm, off_colB, off_colThr, off_colThrIdx,
       off_scalars, off_hkeys, off_hcounts, off_topk_v, off_topk_i, off_part, total_bytes;
   size_t off_hids, off_csum_part, off_csum;   // positives by linearity: class ids, per-block and total class sums
+  size_t off_cls;                             // dense class id of every (padded) column, for the backward's reduce
   int csum_blocks;                            // blocks of tc_class_sum_kernel (256 columns each)
   uint32_t hash_size;
 };
@@ -115,6 +116,11 @@ struct TcBwdPrepArgs {
   const int32_t* labels;
   float *colA, *colAm, *colB, *colThr;
   int32_t *colThrIdx, *lab_pad;
+  // positives by linearity: dense class id of every column (hkeys == nullptr: not wanted)
+  const unsigned long long* hkeys;
+  const int* hids;
+  uint32_t hmask;
+  int32_t* cls_pad;
   float* scalars;
   int n_total, n_pad, topk;
   float tau, alpha, lambda_uni, uni_t;
@@ -141,6 +147,7 @@ struct TcBwdArgs {
   const int* hids;
   uint32_t hmask;
   const float* csum;     // [TC_CMAX][256]
+  const int32_t* cls_pad;  // dense class id per column (tc_prep_bwd_kernel)
   int plin_twin;
 };
 TcPlan tc_plan(const supcon_problem_t* p);

@@ -352,6 +352,7 @@ __global__ void tc_prep_bwd_kernel(TcBwdPrepArgs a) {
     if (j == a.j_lo) { a.scalars[0] = g.cu; a.scalars[1] = -(LOG2E / a.tau) * M; }
   }
   a.colA[j] = A; a.colAm[j] = Am; a.colB[j] = B; a.colThr[j] = thr; a.colThrIdx[j] = ti; a.lab_pad[j] = lab;
+  if (a.hkeys != nullptr) a.cls_pad[j] = j < a.n_total ? label_table_id(a.hkeys, a.hids, a.hmask, lab) : -1;
 }
 
 // ---------------------------------------------------------------------------
@@ -1332,7 +1333,7 @@ __global__ void __launch_bounds__(256) tc_bwd_reduce_kernel(TcBwdArgs a, const _
     // positives by linearity: - sum_{j in pos(i)} (B_i + B_j) z_j = -2 B_i (C[class_i] - z_i), in fp32
     const float Bi = a.colB[gi];
     if (Bi != 0.f) {
-      const int c = label_table_id(a.hkeys, a.hids, a.hmask, a.lab_pad[gi]);
+      const int c = a.cls_pad[gi];
       const float4 cs = *reinterpret_cast<const float4*>(a.csum + c * TD + 4 * c4);
       const __nv_bfloat16* zr = z + (int64_t)gi * TD + 4 * c4;
       const float m = -2.f * Bi;
@@ -1534,6 +1535,7 @@ TcPlan tc_plan(const supcon_problem_t* p) {
   pl.off_hkeys = off; off += (size_t)hsize * 8;      // keys then counts: one memset clears both
   pl.off_hcounts = off; off += (size_t)hsize * 4;
   pl.off_hids = off; off += (size_t)hsize * 4;
+  pl.off_cls = off; off += align_up((size_t)pl.n_pad * 4, 256);
   pl.csum_blocks = (p->n_total + 127) / 128;   // CS_COLS columns per block
   pl.off_csum = off; off += (size_t)TC_CMAX * TD * sizeof(float);
   pl.off_csum_part = off; off += align_up((size_t)pl.csum_blocks * TC_CMAX * TD * sizeof(float), 256);
@@ -1901,7 +1903,10 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
                     ((long long)p->n_rows * p->n_total >= (1ll << 30) || (p->flags & SUPCON_FLAG_CLASS_SUMS));
   int* n_classes = reinterpret_cast<int*>(ws) + WS_NCLASSES_WORD;
   int* hids = reinterpret_cast<int*>(ws + pl.off_hids);
-  if (plin) {
+  // the forward of the same problem left its label table and class sums in this very workspace (caller's promise)
+  const bool from_fwd = plin && (p->flags & SUPCON_FLAG_WS_FROM_FORWARD) && fwd_class_sums(p, 0) &&
+                        !(p->flags & (SUPCON_FLAG_DEBUG_TC_FWD_ONLY | SUPCON_FLAG_DEBUG_TC_BWD_ONLY));
+  if (plin && !from_fwd) {
     e = cudaMemsetAsync(workspace, 0, 256, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ws + pl.off_hkeys, 0, (size_t)pl.hash_size * 12, stream);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
@@ -1928,6 +1933,9 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   pa.scalars = reinterpret_cast<float*>(ws + pl.off_scalars);
   pa.n_total = p->n_total; pa.n_pad = pl.n_pad; pa.topk = p->topk;
   pa.tau = p->tau; pa.alpha = p->alpha; pa.lambda_uni = p->lambda_uni; pa.uni_t = p->uni_t;
+  pa.hkeys = plin ? reinterpret_cast<const unsigned long long*>(ws + pl.off_hkeys) : nullptr;
+  pa.hids = hids; pa.hmask = pl.hash_size - 1;
+  pa.cls_pad = reinterpret_cast<int32_t*>(ws + pl.off_cls);
   tc_prep_bwd_kernel<<<(pa.j_cnt + 255) / 256, 256, 0, stream>>>(pa);
   e = cudaGetLastError();
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return (int)e; }
@@ -1955,6 +1963,7 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
   a.hkeys = reinterpret_cast<const unsigned long long*>(ws + pl.off_hkeys);
   a.hids = hids; a.hmask = pl.hash_size - 1;
   a.csum = reinterpret_cast<const float*>(ws + pl.off_csum);
+  a.cls_pad = pa.cls_pad;
   a.plin_twin = 0;
   const size_t smem = 6 * (size_t)NBOX * 64 * 128 + 1024;   // 6 x 32 KB Z_J stages
   const int ctas = a.sched.P;

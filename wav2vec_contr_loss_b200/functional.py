@@ -30,6 +30,29 @@ def _stream(dev) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+class _NoSwitch:
+    """Stand-in for torch.cuda.device(dev) when dev already is the current device (the usual case: one process per
+    GPU): entering torch's context manager costs ~8 us per call, more than a whole launch at the native batch."""
+    __slots__ = ()
+
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on(dev):
+    """Context in which ``dev`` is the current CUDA device."""
+    idx = dev.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(dev)
+
+
 def _dtype_id(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return _cabi.F32
@@ -86,7 +109,7 @@ def canonical_labels(labels: torch.Tensor, n: int) -> torch.Tensor:
         return keys
     lib = _cabi.load()
     dev = lab.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         keys = torch.empty(n, dtype=torch.int32, device=dev)
         _cabi.check(lib.supcon_label_keys(_p(lab), code, n, _p(keys), _stream(dev)), "supcon_label_keys")
     return keys
@@ -151,17 +174,40 @@ def _stats_buffers(n_rows: int, dev, want_loss: bool = True):
     return stats, partials, loss
 
 
-def forward_rows(z_all: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Problem, want_loss: bool):
-    """Row-block forward. Returns (row_stats [n_rows,8] f32, partials [8] f64, loss or None)."""
+_WITH_FLAGS = {}
+
+
+def with_flags(prob: _cabi.Problem, extra: int) -> _cabi.Problem:
+    """The same problem with ``extra`` OR-ed into its flags (cached: host structs are immutable once built)."""
+    key = (_problem_key(prob), int(extra))
+    out = _WITH_FLAGS.get(key)
+    if out is None:
+        out = _cabi.Problem(n_total=prob.n_total, row_offset=prob.row_offset, n_rows=prob.n_rows, d=prob.d,
+                            z_dtype=prob.z_dtype, similarity=prob.similarity, topk=prob.topk,
+                            flags=prob.flags | int(extra), tau=prob.tau, alpha=prob.alpha,
+                            lambda_uni=prob.lambda_uni, uni_t=prob.uni_t)
+        if len(_WITH_FLAGS) > 4096:
+            _WITH_FLAGS.clear()
+        _WITH_FLAGS[key] = out
+    return out
+
+
+def forward_rows(z_all: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Problem, want_loss: bool,
+                 keep_ws: bool = False):
+    """Row-block forward. Returns (row_stats [n_rows,8] f32, partials [8] f64, loss or None) and, with
+    ``keep_ws``, the workspace as a fourth item: handed to backward_rows(ws=...) untouched, it lets the backward
+    reuse the label table and class sums the forward built (SUPCON_FLAG_WS_FROM_FORWARD)."""
     _require_cuda(z_all, "z")
     lib = _cabi.load()
     dev = z_all.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         stats, partials, loss = _stats_buffers(prob.n_rows, dev, want_loss)
         ws = workspace_for(prob, dev)
         _cabi.check(lib.supcon_forward_rows(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(stats),
                                             _p(partials), _p(loss), _p(ws), ws.numel(), _stream(dev)),
                     "supcon_forward_rows")
+    if keep_ws:
+        return stats, partials, loss, ws
     return stats, partials, loss
 
 
@@ -172,7 +218,7 @@ def loss_and_grad(z: torch.Tensor, labels_i32: torch.Tensor, prob: _cabi.Problem
     _require_cuda(z, "z")
     lib = _cabi.load()
     dev = z.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         stats, partials, loss = _stats_buffers(prob.n_rows, dev, True)
         dz = torch.empty((prob.n_rows, prob.d), dtype=out_dtype, device=dev) if want_grad else None
         ws = workspace_for(prob, dev)
@@ -193,7 +239,7 @@ def forward_rows_local(z_all, labels_i32, prob: _cabi.Problem) -> torch.Tensor:
     _require_cuda(z_all, "z")
     lib = _cabi.load()
     dev = z_all.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = workspace_for(prob, dev)
         _cabi.check(lib.supcon_forward_rows_local(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(ws), ws.numel(),
                                                   _stream(dev)), "supcon_forward_rows_local")
@@ -204,7 +250,7 @@ def forward_rows_remote(z_all, labels_i32, prob: _cabi.Problem, ws: torch.Tensor
     """Phase 2: all other columns + merge. Returns (row_stats, partials) like forward_rows."""
     lib = _cabi.load()
     dev = z_all.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         stats, partials, _ = _stats_buffers(prob.n_rows, dev, False)
         _cabi.check(lib.supcon_forward_rows_remote(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(stats),
                                                    _p(partials), _p(ws), ws.numel(), _stream(dev)),
@@ -215,7 +261,7 @@ def forward_rows_remote(z_all, labels_i32, prob: _cabi.Problem, ws: torch.Tensor
 def finalize(prob: _cabi.Problem, partials_global: torch.Tensor) -> torch.Tensor:
     lib = _cabi.load()
     dev = partials_global.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         loss = torch.empty((), dtype=torch.float32, device=dev)
         _cabi.check(lib.supcon_finalize(ctypes.byref(prob), _p(partials_global), _p(loss), _stream(dev)),
                     "supcon_finalize")
@@ -227,7 +273,7 @@ def finalize_sets(prob: _cabi.Problem, partial_sets: torch.Tensor):
     Returns (partials_global [8] f64, loss)."""
     lib = _cabi.load()
     dev = partial_sets.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         out = torch.empty(_cabi.N_PARTIALS + 1, dtype=torch.float64, device=dev)
         partials, loss = out[:_cabi.N_PARTIALS], out[_cabi.N_PARTIALS:].view(torch.float32)[0]
         _cabi.check(lib.supcon_finalize_sets(ctypes.byref(prob), _p(partial_sets), partial_sets.numel() // _cabi.N_PARTIALS,
@@ -240,7 +286,7 @@ def peer_push(desc: _cabi.Peer, src0: torch.Tensor, dst_off0: int, src1, dst_off
     """supcon_peer_push: src0 (and src1) -> the same byte offsets of every peer's exchange buffer, then the flag."""
     lib = _cabi.load()
     dev = src0.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         _cabi.check(lib.supcon_peer_push(ctypes.byref(desc), _p(src0), src0.numel() * src0.element_size(), int(dst_off0),
                                          _p(src1), 0 if src1 is None else src1.numel() * src1.element_size(),
                                          int(dst_off1), int(flag_id), int(wait_flag_id), 1 if include_self else 0,
@@ -251,7 +297,7 @@ def peer_wait(desc: _cabi.Peer, flag_id: int, device, rank_mask=None):
     """Block the stream until the flag of every rank (or of the ranks in rank_mask) carries the current step."""
     lib = _cabi.load()
     mask = (1 << 64) - 1 if rank_mask is None else int(rank_mask)
-    with torch.cuda.device(device):
+    with _on(device):
         _cabi.check(lib.supcon_peer_wait_mask(ctypes.byref(desc), int(flag_id), ctypes.c_uint64(mask), _stream(device)),
                     "supcon_peer_wait_mask")
 
@@ -262,7 +308,7 @@ def peer_push_ordered(desc: _cabi.Peer, src0: torch.Tensor, dst_off0: int, src1,
     its copy is complete."""
     lib = _cabi.load()
     dev = src0.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         _cabi.check(lib.supcon_peer_push_ordered(ctypes.byref(desc), _p(src0), src0.numel() * src0.element_size(),
                                                  int(dst_off0), _p(src1),
                                                  0 if src1 is None else src1.numel() * src1.element_size(),
@@ -287,7 +333,7 @@ def forward_rows_pass(z_all, labels_i32, prob: _cabi.Problem, passes: ForwardPas
     (row_stats, partials) (last pass)."""
     lib = _cabi.load()
     dev = z_all.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         if ws is None:
             ws = workspace_for(prob, dev)
         last = index == passes.n - 1
@@ -303,7 +349,7 @@ def forward_rows_pass(z_all, labels_i32, prob: _cabi.Problem, passes: ForwardPas
 
 def peer_end_step(desc: _cabi.Peer, flag_id: int, device):
     lib = _cabi.load()
-    with torch.cuda.device(device):
+    with _on(device):
         _cabi.check(lib.supcon_peer_end_step(ctypes.byref(desc), int(flag_id), _stream(device)), "supcon_peer_end_step")
 
 
@@ -312,7 +358,7 @@ def backward_rows_local(z_all, labels_i32, stats_local, partials_local, prob: _c
     (no exchange needed yet, no grad_out needed yet).  Returns the workspace backward_rows_remote must be given."""
     lib = _cabi.load()
     dev = z_all.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = workspace_for(prob, dev)
         _cabi.check(lib.supcon_backward_rows_local(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(stats_local),
                                                    _p(partials_local), _p(ws), ws.numel(), _stream(dev)),
@@ -325,7 +371,7 @@ def backward_rows_remote(z_all, labels_i32, stats_all, partials_global, grad_out
     """Phase 2: all other columns + sum of both phases, scaled by grad_out."""
     lib = _cabi.load()
     dev = z_all.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         dz = torch.empty((prob.n_rows, prob.d), dtype=out_dtype, device=dev)
         g = None
         if grad_out is not None:
@@ -338,12 +384,17 @@ def backward_rows_remote(z_all, labels_i32, stats_all, partials_global, grad_out
 
 
 def backward_rows(z_all, labels_i32, stats_all, partials_global, grad_out, prob: _cabi.Problem,
-                  out_dtype=torch.float32) -> torch.Tensor:
+                  out_dtype=torch.float32, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``ws``: the workspace forward_rows(..., keep_ws=True) returned for the SAME problem, untouched since (the
+    backward then reuses what the forward built there); None = a fresh one."""
     lib = _cabi.load()
     dev = z_all.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         dz = torch.empty((prob.n_rows, prob.d), dtype=out_dtype, device=dev)
-        ws = workspace_for(prob, dev)
+        if ws is None:
+            ws = workspace_for(prob, dev)
+        else:
+            prob = with_flags(prob, _cabi.FLAG_WS_FROM_FORWARD)
         g = None
         if grad_out is not None:
             g = grad_out.detach().reshape(()).to(device=dev, dtype=torch.float32)
@@ -357,7 +408,7 @@ def backward_rows(z_all, labels_i32, stats_all, partials_global, grad_out, prob:
 def topk_indices(z_all, labels_i32, row_stats, prob: _cabi.Problem) -> torch.Tensor:
     lib = _cabi.load()
     dev = z_all.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         idx = torch.empty((prob.n_rows, prob.topk), dtype=torch.int32, device=dev)
         _cabi.check(lib.supcon_topk_indices(ctypes.byref(prob), _p(z_all), _p(labels_i32), _p(row_stats),
                                             _p(idx), _stream(dev)), "supcon_topk_indices")
@@ -391,11 +442,14 @@ class SupConFunction(torch.autograd.Function):
             ctx.fused = True
             ctx.in_dtype = z.dtype
             return _loss_dtype(loss, z.dtype)
-        stats, partials, loss = forward_rows(zc, labels_i32, prob, want_loss=True)
         if ctx.needs_input_grad[0]:
-            ctx.save_for_backward(zc, labels_i32, stats, partials)
+            # the workspace stays alive until the backward, which reuses the label table / class sums left in it
+            stats, partials, loss, ws = forward_rows(zc, labels_i32, prob, want_loss=True, keep_ws=True)
+            ctx.save_for_backward(zc, labels_i32, stats, partials, ws)
             ctx.prob = prob
             ctx.in_dtype = z.dtype
+        else:
+            stats, partials, loss = forward_rows(zc, labels_i32, prob, want_loss=True)
         return _loss_dtype(loss, z.dtype)
 
     @staticmethod
@@ -403,9 +457,9 @@ class SupConFunction(torch.autograd.Function):
         if ctx.fused:
             (dz,) = ctx.saved_tensors
             return (dz * grad_out.to(dz.dtype)).to(ctx.in_dtype), None, None, None, None, None, None, None, None
-        zc, labels_i32, stats, partials = ctx.saved_tensors
+        zc, labels_i32, stats, partials, ws = ctx.saved_tensors
         out_dtype = zc.dtype
-        dz = backward_rows(zc, labels_i32, stats, partials, grad_out, ctx.prob, out_dtype=out_dtype)
+        dz = backward_rows(zc, labels_i32, stats, partials, grad_out, ctx.prob, out_dtype=out_dtype, ws=ws)
         return dz.to(ctx.in_dtype), None, None, None, None, None, None, None, None
 
 
@@ -464,7 +518,7 @@ class _NormalizeFunction(torch.autograd.Function):
         xc = x.detach().float().contiguous()
         n, d = xc.shape
         dev = xc.device
-        with torch.cuda.device(dev):
+        with _on(dev):
             z = torch.empty((n, d), dtype=out_dtype, device=dev)
             norms = torch.empty(n, dtype=torch.float32, device=dev)
             _cabi.check(lib.supcon_normalize_forward(_p(xc), n, d, _p(z), _dtype_id(z), _p(norms), _stream(dev)),
@@ -482,7 +536,7 @@ class _NormalizeFunction(torch.autograd.Function):
         dz = dz.contiguous()
         n, d = z.shape
         dev = z.device
-        with torch.cuda.device(dev):
+        with _on(dev):
             dx = torch.empty((n, d), dtype=torch.float32, device=dev)
             _cabi.check(lib.supcon_normalize_backward(_p(z), _dtype_id(z), _p(norms), _p(dz), _dtype_id(dz),
                                                       n, d, _p(dx), _stream(dev)),
