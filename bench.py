@@ -429,7 +429,7 @@ def main():
     class_sums = args.similarity == "cosine" and args.alpha == 0.0
     bwd_plin = class_sums and n_local * n >= (1 << 30)
     bwd_extra = 4 if bwd_plin else 0
-    launches_per_step = (7 + (3 if class_sums else 0) + (1 if bwd_plin else 0)) if world == 1 else 14
+    launches_per_step = (7 + (4 if bwd_plin else 0)) if world == 1 else 14   # fwd +3, bwd +1 (its twin)
     launches = {"count": 0}
 
     def step(z_loc, y_loc):

@@ -57,8 +57,8 @@ extern "C" {
 #define SUPCON_FLAG_PEER_EXCHANGE 64u
 /* Tensor-core path, cosine similarity without mining: the positives' terms (sum of s_ij over a row's positives in
  * the forward, -sum (B_i + B_j) z_j in the backward) are linear in z_j and can be formed from per-class sums of
- * the rows, O(N d), instead of per pair in the sweep.  The library takes that route where it pays (whole-batch
- * forward; backward of at least 2^30 pairs; at most 32 classes, decided on the device).  These two flags pin the
+ * the rows, O(N d), instead of per pair in the sweep.  The library takes that route where it pays (single-phase
+ * forward / backward of at least 2^30 pairs; at most 32 classes, decided on the device).  These two flags pin the
  * choice: CLASS_SUMS = also for small problems, NO_CLASS_SUMS = never. */
 #define SUPCON_FLAG_CLASS_SUMS 128u
 #define SUPCON_FLAG_NO_CLASS_SUMS 256u

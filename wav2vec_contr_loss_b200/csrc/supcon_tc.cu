@@ -1672,10 +1672,16 @@ static cudaError_t fwd_launch_kernel(const supcon_problem_t* p, const CUtensorMa
   return launch_fwd_m<SUPCON_COSINE, false>(mine, tm, zb, a, ctas, smem, stream);
 }
 
-// positives by linearity in the forward: whole forward (one phase), cosine, no mining
+// The class-sum route costs ~45 us (forward) / ~30 us (backward) of small kernels and saves ~9 % of a sweep: it pays
+// from about 2^30 pairs per launch (a quarter of the N = 65536 batch) upwards.
+constexpr long long PLIN_MIN_PAIRS = 1ll << 30;
+static bool plin_size_ok(const supcon_problem_t* p) {
+  return (long long)p->n_rows * p->n_total >= PLIN_MIN_PAIRS || (p->flags & SUPCON_FLAG_CLASS_SUMS);
+}
+// positives by linearity in the forward: whole forward (one phase), cosine, no mining, large enough
 static bool fwd_class_sums(const supcon_problem_t* p, int phase) {
   return phase == 0 && p->similarity == SUPCON_COSINE && !(p->alpha != 0.f && p->topk >= 1) &&
-         knobs().fwd_plin != 0 && !(p->flags & SUPCON_FLAG_NO_CLASS_SUMS);
+         knobs().fwd_plin != 0 && !(p->flags & SUPCON_FLAG_NO_CLASS_SUMS) && plin_size_ok(p);
 }
 
 int tc_forward(const supcon_problem_t* p, const void* z_all, const int32_t* labels_all, float* row_stats,
@@ -1895,12 +1901,10 @@ int tc_backward(const supcon_problem_t* p, const void* z_all, const int32_t* lab
                                                    reinterpret_cast<float*>(ws + pl.off_nrm),
                                                    reinterpret_cast<unsigned*>(ws + pl.off_scalars) + 8, pl.n_pad);
   }
-  // positives by linearity: single-phase cosine backward without mining, when the sweep is long enough for its
-  // ~7 % to outweigh the ~30 us of class-sum kernels (a rank's share of at least 2^30 pairs)
+  // positives by linearity: single-phase cosine backward without mining, when the sweep is long enough
   const bool mine_b = p->alpha != 0.f && p->topk >= 1;
   const bool plin = phase == 0 && p->similarity == SUPCON_COSINE && !mine_b && knobs().bwd_plin != 0 &&
-                    !(p->flags & SUPCON_FLAG_NO_CLASS_SUMS) &&
-                    ((long long)p->n_rows * p->n_total >= (1ll << 30) || (p->flags & SUPCON_FLAG_CLASS_SUMS));
+                    !(p->flags & SUPCON_FLAG_NO_CLASS_SUMS) && plin_size_ok(p);
   int* n_classes = reinterpret_cast<int*>(ws) + WS_NCLASSES_WORD;
   int* hids = reinterpret_cast<int*>(ws + pl.off_hids);
   // the forward of the same problem left its label table and class sums in this very workspace (caller's promise)
