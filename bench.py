@@ -9,9 +9,12 @@ unit-norm embeddings (value = N^2 / t).  Default workload = BASELINE.json
 configs[3], the largest single-GPU configuration the metric is quoted on:
 cosine SupCon, tau 0.07, N = 65536, d = 256, bf16 z / fp32-or-bf16 dz.  With
 --gpus R > 1 (launched by torchrun) the N rows are sharded over the ranks
-(strong scaling at fixed N): all-gather z/labels overlapped with the forward over
-the rank's own columns -> the other columns -> all-gather of row statistics and
-partial sums overlapped with the backward over the own columns -> the rest.
+(strong scaling at fixed N, the BASELINE config): rows and labels pushed into
+every peer's buffer (or all-gathered) beside the forward over the rank's own
+columns -> the other columns -> exchange of row statistics and partial sums ->
+backward.  The same run then measures the step once more at WEAK scaling
+(N = batch-n * sqrt(R), the per-GPU pair count of the single-GPU workload: the
+north_star's 8-GPU target is a weak-scaling one) and reports it under "weak".
 The timed call is the drop-in module itself (SupConBinaryLoss / ShardedSupConLoss
 called as stage1_utils.py:125-128 calls the reference's) + autograd.
 

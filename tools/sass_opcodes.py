@@ -22,7 +22,7 @@ for line in sass.splitlines():
     m = re.match(r"\s*/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
     if m and cur is not None:
         cur[m.group(1)] += 1
-KEY = ("UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "UTMALDG", "UTMAPF", "SYNCS", "MUFU", "FFMA", "HMMA", "LDGSTS")
+KEY = ("UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "UTMALDG", "UTMAPF", "SYNCS", "MUFU", "FFMA", "FFMA2", "FADD2", "FMUL2", "HMMA", "LDGSTS")
 print(f"# cuobjdump -sass {os.path.relpath(lib, ROOT)} -- instruction counts per kernel (static SASS)")
 print(f"# {'kernel':70s} {'total':>7s} " + " ".join(f"{k:>8s}" for k in KEY))
 tot = collections.Counter()
