@@ -168,6 +168,11 @@ def test_graphed_step_with_fused_head_and_dropout(cuda_device):
     y = (torch.randperm(64, generator=g) % 2).to(cuda_device)
     hs = (torch.randn(64, 3, 64, 20, generator=g).to(cuda_device) + 0.6 * (2.0 * y.view(-1, 1, 1, 1) - 1.0))
     opt = torch.optim.AdamW(head.parameters(), lr=1e-2, capturable=True)
+    # an eager twin: same weights, same dropout stream (seed and offset), same optimizer
+    import copy
+    head_e = copy.deepcopy(head)
+    opt_e = torch.optim.AdamW(head_e.parameters(), lr=1e-2, capturable=True)
+    twin = S.GraphedHeadStep(head_e, SupConBinaryLoss(0.1, "cosine"), opt_e, hs, y, topk_neg=7)
     step = S.GraphedHeadStep(head, SupConBinaryLoss(0.1, "cosine"), opt, hs, y, topk_neg=7)
     before = torch.cat([p.detach().reshape(-1) for p in head.parameters()]).clone()
     step._graphs[0.0] = step._capture(0.0)
@@ -178,3 +183,12 @@ def test_graphed_step_with_fused_head_and_dropout(cuda_device):
     # the classes are well separated, so the loss starts close to its floor log(|pos|) = log 31 = 3.434
     assert all(l == l for l in losses) and sum(losses[-5:]) < sum(losses[:5]) - 0.01
     assert min(losses) > 3.43
+    # the 25 replays walked the trajectory of 25 eager steps with the same dropout offsets: a replay that stopped
+    # updating the weights, or drew the same mask every time, would not
+    eager = [float(twin._eager(0.0)) for _ in range(25)]
+    assert head_e.rng_state.tolist() == head.rng_state.tolist()
+    assert losses == pytest.approx(eager, rel=1e-4)
+    flat_g = torch.cat([p.detach().reshape(-1) for p in head.parameters()])
+    flat_e = torch.cat([p.detach().reshape(-1) for p in head_e.parameters()])
+    assert not torch.equal(flat_g, before)
+    assert torch.allclose(flat_g, flat_e, rtol=1e-3, atol=1e-5)
