@@ -466,3 +466,12 @@ def test_tensor_path_positive_sums_for_any_class_count(cuda_device, classes, lam
     assert torch.equal(outs["class_sums"][1][:, _cabi.ST_LSE], outs["per_pair"][1][:, _cabi.ST_LSE])
     if float(want["dz"].norm()) > 1e-9:
         assert G.rel_err(outs["class_sums"][2], outs["per_pair"][2]) < TOL_BF16
+    # through the module with the class-sum route pinned: the backward takes the label table and the class sums
+    # out of the workspace the forward left (SUPCON_FLAG_WS_FROM_FORWARD) instead of rebuilding them
+    loss_m, dz_m = G.kernel_loss_and_grad(zb, y, tau=tau, similarity="cosine", lam=lam, topk=15, alpha=0.0,
+                                          dtype=torch.bfloat16, device=cuda_device, unit_rows=True,
+                                          flags=_cabi.FLAG_CLASS_SUMS)
+    assert loss_m == pytest.approx(outs["class_sums"][0], rel=1e-6)
+    if float(want["dz"].norm()) > 1e-9:
+        assert G.rel_err(dz_m, want["dz"]) < 2 * TOL_BF16                  # dz rounded to bf16 by autograd
+        assert G.rel_err(dz_m, outs["class_sums"][2]) < 4e-3               # = the bf16 rounding of the same gradient
