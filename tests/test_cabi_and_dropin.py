@@ -35,6 +35,39 @@ def test_library_exports_every_declared_symbol(lib_built):
     assert hasattr(debug_lib.load(), "supcon_debug_plan") and hasattr(debug_lib.load(), "supcon_forward_rows")
 
 
+def test_flag_constants_match_the_header():
+    """every SUPCON_FLAG_* of the public header that the Python binding names carries the header's value"""
+    from wav2vec_contr_loss_b200 import _cabi
+    text = open(os.path.join(ROOT, "include", "supcon_b200.h")).read()
+    defines = {k: int(v) for k, v in re.findall(r"#define\s+SUPCON_FLAG_([A-Z_]+)\s+(\d+)u", text)}
+    assert {"FORCE_EXACT", "FORCE_TENSOR", "NO_SMALL", "UNIT_ROWS", "PEER_EXCHANGE", "CLASS_SUMS", "NO_CLASS_SUMS",
+            "WS_FROM_FORWARD"} <= set(defines)
+    vals = sorted(defines.values())
+    assert len(set(vals)) == len(vals) and all(v & (v - 1) == 0 for v in vals)       # distinct single bits
+    for name, value in defines.items():
+        if hasattr(_cabi, "FLAG_" + name):
+            assert getattr(_cabi, "FLAG_" + name) == value, name
+    for name in ("CLASS_SUMS", "NO_CLASS_SUMS", "WS_FROM_FORWARD", "UNIT_ROWS", "PEER_EXCHANGE"):
+        assert hasattr(_cabi, "FLAG_" + name), name
+
+
+def test_tensor_path_workspace_is_flag_independent(lib_built):
+    """the workspace of a problem does not depend on the route flags (a forward's workspace may be handed to the
+    backward of the same problem with SUPCON_FLAG_WS_FROM_FORWARD set)"""
+    from wav2vec_contr_loss_b200 import _cabi
+    from wav2vec_contr_loss_b200.functional import make_problem, with_flags
+    lib = _cabi.load()
+    sizes = []
+    base = make_problem(4096, 256, _cabi.BF16, tau=0.07, similarity=_cabi.COSINE, flags=_cabi.FLAG_UNIT_ROWS)
+    for extra in (0, _cabi.FLAG_CLASS_SUMS, _cabi.FLAG_NO_CLASS_SUMS, _cabi.FLAG_WS_FROM_FORWARD):
+        nbytes = ctypes.c_size_t(0)
+        prob = with_flags(base, extra)
+        assert prob.flags == base.flags | extra and prob.n_total == 4096
+        assert lib.supcon_workspace_bytes(ctypes.byref(prob), ctypes.byref(nbytes)) == 0
+        sizes.append(nbytes.value)
+    assert len(set(sizes)) == 1 and sizes[0] > 4096 * 256 * 4     # holds at least one fp32 dz record
+
+
 def test_argument_validation_without_gpu(lib_built):
     from wav2vec_contr_loss_b200 import _cabi
     from wav2vec_contr_loss_b200.functional import make_problem
