@@ -1,6 +1,11 @@
-"""Rough host-side cost of one N = 64 fwd+bwd through the module: CPU tensors, every C call stubbed out (runs without a GPU).
-import sys, time, types, ctypes
-sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""Rough host-side cost of one N = 64 fwd+bwd through the module: CPU tensors, every C call stubbed out
+(runs without a GPU; the numbers say where the Python-side time of a call goes, not what the kernels cost)."""
+import ctypes
+import os
+import sys
+import time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from wav2vec_contr_loss_b200 import functional as Fn, _cabi
 from wav2vec_contr_loss_b200.loss import SupConBinaryLoss
