@@ -16,8 +16,12 @@
 //              TMEM, then dZ_I += H_IJ Z_J (tcgen05 128x256x16, the same smem Z_J tile
 //              consumed MN-major) accumulates in TMEM.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM
-// alloc), warps 2..9 = eight softmax/epilogue warps (two warpgroups).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), then 8 * NCH softmax / epilogue warps
+// (NCH = threads sharing one tile row: 320 or 576 threads per CTA, see tc_threads()).
+// Round 2 took three things out of the O(N^2) hot loops of the cosine sweeps (each measured, profiles/r02_*.md):
+// the positives' terms (linear in z_j: formed from O(N d) class sums, template flag PLIN), half of the issue
+// slots of the fp32 arithmetic (packed pairs, FFMA2 / FADD2 / FMUL2) and, with two threads per row, half of each
+// warp's dependent instruction stream.
 // Preconditions of this path (checked by the dispatcher): bf16 z, d == 256, tau >= 0.025 and, for cosine
 // similarity, the caller's promise SUPCON_FLAG_UNIT_ROWS (geodesic similarities lie in [-1, 1] whatever the
 // norms).  The exponentials use ONE fixed maximum M = max(1, max_j |z_j|^2) (every similarity is <= M by
@@ -1058,6 +1062,9 @@ __device__ __forceinline__ int bwd_col_tile(const TcBwdArgs& a, int ct) {
 // what holds the pipe at ~75 %.  What the variants share is the shared-memory traffic per tile: 32 KB read by
 // the S MMAs + 32 KB by the dZ MMAs + 32 KB written by TMA = 94 B/clk of the 128 B/clk port; sharing Z_J
 // between two CTAs (cta_group::2) is the remaining lever.
+// Later in round 2 the chain itself got shorter instead -- the positives' term left the loop (PLIN) and the fp32
+// arithmetic went to packed pairs: 1433 M -> ~930 M instructions, tensor pipe 73.5 % -> 80.9 %, 3.19 -> 2.87 ms
+// (profiles/r02_fwd_pos_by_linearity.md, r02_packed_pairs_ab.md).
 template <int SIM, bool UNI, bool MINE, int NCH, bool PLIN>
 __global__ void __launch_bounds__(tc_threads(NCH), 1) tc_bwd_kernel(const __grid_constant__ CUtensorMap tmapJ,
                                                                     const __nv_bfloat16* __restrict__ z, TcBwdArgs a) {
