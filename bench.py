@@ -716,7 +716,7 @@ def main():
                          "note": "same module call; eager = issued from Python every step, wall clock with a final sync, "
                                  "no L2 flush between iterations (the graph figure flushes L2 before every step)"},
             "gpu_launches": n_launch,
-            "roofline": {"bound": "tensor", "kernel": "tc_bwd_kernel + its prep/reduce (recompute S, dz = (G+G^T) z)",
+            "roofline": {"bound": "tensor", "kernel": "tc_bwd_kernel + its O(N) kernels (class sums, prep, reduce): recompute S, dz = (G+G^T) z",
                          "achieved": bwd_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": bwd_tflops / pk["tflops"], "traffic": traffic_bytes("tc_bwd_kernel", args, world),
                          "peak_source": pk["source"],
